@@ -1,0 +1,385 @@
+// Edge-depth solve (forward, top-k selection, backward) for sm_100a.
+//
+// Replaces DGDE/model/anno_encoder.py:313-390 (decode_pairs_kpts_depth + get_up) and the solve/top-k of
+// GMW/main.py:351-416 (compute_z).  Design:
+//   * one CTA works on one object at a time (persistent grid-stride loop over objects);
+//   * the object's keypoints (2D v, 3D X/Y/Z, yaw, intrinsics: ~1.5 KB) are read from HBM once, reduced
+//     to 16 B of per-keypoint terms {v, Y, v*C, C} and staged in shared memory (double buffered, one
+//     __syncthreads per object);
+//   * every thread owns a FIXED set of edges, so for the production shape (n = 73) the (i,j) pairs live
+//     in registers for the whole kernel; edges are never materialised as an n x n matrix;
+//   * per-object sums use warp shuffles + a fixed-order cross-warp sum (deterministic).
+#include "dcd_common.cuh"
+
+namespace dcd {
+
+namespace {
+
+struct ObjScalars {
+    float s, c, cy, fy, b3;
+};
+
+// Stage one object's per-keypoint terms into shared memory.
+template <int THREADS>
+__device__ __forceinline__ float stage_object(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                                              const float* __restrict__ rot, const float* __restrict__ K,
+                                              int64_t obj, int n, int flags, float4* kp_s) {
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    float cy = 0.f, fy = 1.f, b3 = 0.f;
+    if (K != nullptr) {
+        const float* Ko = K + obj * 12;
+        if (normalise) { cy = __ldg(Ko + 6); fy = __ldg(Ko + 5); }
+        if (flags & DCD_SUB_B3) b3 = __ldg(Ko + 11);
+    }
+    if ((int)threadIdx.x < ((n + 31) & ~31)) {   // only the warps that own keypoints evaluate sin/cos
+        const float r = __ldg(rot + obj);
+        const float s = sinf(r), c = cosf(r);
+        for (int t = threadIdx.x; t < n; t += THREADS) {
+            const float2 uv = __ldg(reinterpret_cast<const float2*>(kps + (obj * n + t) * 2));
+            const float* p3 = kps3d + (obj * n + t) * 3;
+            kp_s[t] = keypoint_terms(uv.y, __ldg(p3), __ldg(p3 + 1), __ldg(p3 + 2), s, c, normalise, cy, fy);
+        }
+    }
+    return b3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: per-edge depths and/or per-object mean
+// NK > 0: compile-time keypoint count, (i,j) of the thread's edges held in registers.
+// NK == 0: any n <= 256, (i,j) from a shared-memory table built once per CTA.
+// ---------------------------------------------------------------------------------------------
+template <int NK, int THREADS, bool WRITE_EDGES>
+__global__ void __launch_bounds__(THREADS)
+edge_solve_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                      const float* __restrict__ rot, const float* __restrict__ K,
+                      int64_t N, int n_rt, float lo, float hi, int flags,
+                      float* __restrict__ depth_edges, float* __restrict__ depth_mean) {
+    constexpr int NWARP = THREADS / 32;
+    const int n = NK > 0 ? NK : n_rt;
+    const int E = n * (n - 1) / 2;
+    constexpr int EPT = NK > 0 ? (NK * (NK - 1) / 2 + THREADS - 1) / THREADS : 1;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* kp_s = reinterpret_cast<float4*>(smem_raw);                       // [2][n]
+    float* part_s = reinterpret_cast<float*>(kp_s + 2 * n);                   // [2][NWARP]
+    uint16_t* tab_s = reinterpret_cast<uint16_t*>(part_s + 2 * NWARP);        // [E] (generic only)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    uint32_t pr[EPT];     // byte offsets (i*16) | (j*16) << 16 of this thread's edges
+    if (NK > 0) {
+#pragma unroll
+        for (int m = 0; m < EPT; ++m) {
+            const int e = tid + m * THREADS;
+            int i = 0, j = 1;
+            if (e < E) decode_edge(e, n, i, j);
+            pr[m] = (uint32_t)(i * 16) | ((uint32_t)(j * 16) << 16);
+        }
+    } else {
+        for (int e = tid; e < E; e += THREADS) {
+            int i, j;
+            decode_edge(e, n, i, j);
+            tab_s[e] = (uint16_t)((i << 8) | j);
+        }
+        // visibility is ordered by the first __syncthreads of the object loop
+    }
+
+    int buf = 0;
+    int64_t prev = -1;
+    float prev_b3 = 0.f;
+    (void)prev_b3;
+    for (int64_t obj = blockIdx.x; obj < N; obj += gridDim.x) {
+        float4* kp = kp_s + buf * n;
+        const float b3 = stage_object<THREADS>(kps, kps3d, rot, K, obj, n, flags, kp);
+        __syncthreads();
+        if (depth_mean != nullptr && tid == 0 && prev >= 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) t += part_s[(buf ^ 1) * NWARP + w];
+            depth_mean[prev] = __fdiv_rn(t, (float)E);
+        }
+        float acc = 0.f;
+        const unsigned char* kpb = reinterpret_cast<const unsigned char*>(kp);
+        float* out = WRITE_EDGES ? depth_edges + obj * (int64_t)E : nullptr;
+        if (NK > 0) {
+#pragma unroll
+            for (int m = 0; m < EPT; ++m) {
+                const int e = tid + m * THREADS;
+                if (m < EPT - 1 || e < E) {
+                    const float4 a = *reinterpret_cast<const float4*>(kpb + (pr[m] & 0xffffu));
+                    const float4 b = *reinterpret_cast<const float4*>(kpb + (pr[m] >> 16));
+                    const float z = edge_depth(a, b, lo, hi, b3);
+                    if (WRITE_EDGES) __stcs(out + e, z);
+                    acc += z;
+                }
+            }
+        } else {
+            for (int e = tid; e < E; e += THREADS) {
+                const uint32_t p = tab_s[e];
+                const float4 a = kp[p >> 8];
+                const float4 b = kp[p & 0xffu];
+                const float z = edge_depth(a, b, lo, hi, b3);
+                if (WRITE_EDGES) __stcs(out + e, z);
+                acc += z;
+            }
+        }
+        if (depth_mean != nullptr) {
+            acc = warp_sum(acc);
+            if (lane == 0) part_s[buf * NWARP + warp] = acc;
+        }
+        prev = obj;
+        buf ^= 1;
+    }
+    if (depth_mean != nullptr) {
+        __syncthreads();
+        if (tid == 0 && prev >= 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) t += part_s[(buf ^ 1) * NWARP + w];
+            depth_mean[prev] = __fdiv_rn(t, (float)E);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection: top-k edges by |V| sorted (|V| desc, edge id asc) + their depths / pair masks / mean.
+// One CTA per object; bitonic sort of (key, id) in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+edge_select_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                   const float* __restrict__ rot, const float* __restrict__ K,
+                   const uint8_t* __restrict__ kpt_mask, int64_t N, int n, int P, int k,
+                   float lo, float hi, int flags,
+                   int64_t* __restrict__ idx_out, float* __restrict__ depth_sel,
+                   float* __restrict__ mask_sel, float* __restrict__ depth_mean) {
+    constexpr int NWARP = THREADS / 32;
+    const int E = n * (n - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* key_s = reinterpret_cast<uint32_t*>(smem_raw);                  // [P]
+    float4* kp_s = reinterpret_cast<float4*>(key_s + P);                      // [n]
+    float* red_s = reinterpret_cast<float*>(kp_s + n);                        // [NWARP]
+    uint16_t* id_s = reinterpret_cast<uint16_t*>(red_s + NWARP);              // [P]
+    uint8_t* m_s = reinterpret_cast<uint8_t*>(id_s + P);                      // [n]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int64_t obj = blockIdx.x; obj < N; obj += gridDim.x) {
+        __syncthreads();   // previous object's readers are done with shared memory
+        const float b3 = stage_object<THREADS>(kps, kps3d, rot, K, obj, n, flags, kp_s);
+        if (kpt_mask != nullptr)
+            for (int t = tid; t < n; t += THREADS) m_s[t] = kpt_mask[obj * n + t];
+        __syncthreads();
+        // keys: bit pattern of |v_i - v_j| (non-negative floats order like unsigned integers)
+        for (int e = tid; e < P; e += THREADS) {
+            uint32_t key = 0u;
+            uint16_t id = 0xffffu;
+            if (e < E) {
+                int i, j;
+                decode_edge(e, n, i, j);
+                key = __float_as_uint(fabsf(__fsub_rn(kp_s[i].x, kp_s[j].x)));
+                id = (uint16_t)e;
+            }
+            key_s[e] = key;
+            id_s[e] = id;
+        }
+        // bitonic sort, descending by (key, -id)
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int t = tid; t < (P >> 1); t += THREADS) {
+                    const int a = 2 * t - (t & (stride - 1));
+                    const int b = a + stride;
+                    const uint32_t ka = key_s[a], kb = key_s[b];
+                    const uint16_t ia = id_s[a], ib = id_s[b];
+                    const bool a_first = (ka > kb) || (ka == kb && ia < ib);
+                    const bool desc = (a & size) == 0;
+                    if (a_first != desc) {
+                        key_s[a] = kb; key_s[b] = ka;
+                        id_s[a] = ib; id_s[b] = ia;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        float acc = 0.f;
+        for (int r = tid; r < k; r += THREADS) {
+            const int e = id_s[r];
+            int i, j;
+            decode_edge(e, n, i, j);
+            const float z = edge_depth(kp_s[i], kp_s[j], lo, hi, b3);
+            idx_out[obj * k + r] = (int64_t)e;
+            if (depth_sel != nullptr) depth_sel[obj * k + r] = z;
+            if (mask_sel != nullptr) mask_sel[obj * k + r] = (m_s[i] != 0 && m_s[j] != 0) ? 1.f : 0.f;
+            acc += z;
+        }
+        if (depth_mean != nullptr) {
+            acc = warp_sum(acc);
+            if (lane == 0) red_s[warp] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) t += red_s[w];
+                depth_mean[obj] = __fdiv_rn(t, (float)k);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: per-keypoint gather over the n-1 incident edges (deterministic, no atomics)
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+edge_solve_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                      const float* __restrict__ rot, const float* __restrict__ K,
+                      int64_t N, int n, float lo, float hi, int flags,
+                      const int64_t* __restrict__ idx, int k,
+                      const float* __restrict__ grad_depth, const float* __restrict__ grad_mean,
+                      float* __restrict__ grad_kps, float* __restrict__ grad_kps3d) {
+    constexpr int NWARP = THREADS / 32;
+    const int E = n * (n - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* kp_s = reinterpret_cast<float4*>(smem_raw);                       // [n]
+    float* g_s = reinterpret_cast<float*>(kp_s + n);                          // [E] (only when idx != null)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+
+    for (int64_t obj = blockIdx.x; obj < N; obj += gridDim.x) {
+        __syncthreads();
+        stage_object<THREADS>(kps, kps3d, rot, K, obj, n, flags, kp_s);
+        const float r = __ldg(rot + obj);
+        const float sn = sinf(r), cs = cosf(r);
+        const float fy = (normalise && K != nullptr) ? __ldg(K + obj * 12 + 5) : 1.f;
+        const float gm = grad_mean != nullptr ? __fdiv_rn(__ldg(grad_mean + obj), (float)(idx != nullptr ? k : E)) : 0.f;
+        if (idx != nullptr) {
+            for (int e = tid; e < E; e += THREADS) g_s[e] = 0.f;
+            __syncthreads();
+            for (int q = tid; q < k; q += THREADS) {
+                const float g = grad_depth != nullptr ? __ldg(grad_depth + obj * k + q) : 0.f;
+                g_s[(int)idx[obj * k + q]] = g + gm;
+            }
+        }
+        __syncthreads();
+        const float* gd = (idx == nullptr && grad_depth != nullptr) ? grad_depth + obj * (int64_t)E : nullptr;
+        for (int kk = warp; kk < n; kk += NWARP) {
+            const float4 me = kp_s[kk];
+            float gH = 0.f, gV = 0.f;
+            for (int m = lane; m < n; m += 32) {
+                if (m == kk) continue;
+                const int i = min(kk, m), j = max(kk, m);
+                const int e = row_offset(i, n) + j - i - 1;
+                float g;
+                if (idx != nullptr) g = g_s[e];
+                else g = (gd != nullptr ? __ldg(gd + e) : 0.f) + gm;
+                if (g == 0.f) continue;
+                const float4 a = (kk == i) ? me : kp_s[m];
+                const float4 b = (kk == i) ? kp_s[m] : me;
+                const float H = __fadd_rn(__fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z));
+                const float V = __fsub_rn(a.x, b.x);
+                const float aV = fabsf(V);
+                const float Vc = fmaxf(aV, 1e-10f);
+                const float x = __fdiv_rn(fabsf(H), Vc);
+                const bool pass = (x >= lo) && (fmaxf(x, lo) <= hi);
+                if (!pass) continue;
+                const float sH = (H > 0.f) ? 1.f : ((H < 0.f) ? -1.f : 0.f);
+                const float sV = (V > 0.f) ? 1.f : ((V < 0.f) ? -1.f : 0.f);
+                const float dH = g * sH / Vc;
+                const float dV = (aV >= 1e-10f) ? -g * (x / Vc) * sV : 0.f;
+                const float sgn = (kk == i) ? 1.f : -1.f;
+                gH += sgn * dH;
+                gV += sgn * dV;
+            }
+            gH = warp_sum(gH);
+            gV = warp_sum(gV);
+            if (lane == 0) {
+                const float gv = gV + gH * me.w;          // d/dv: V and the v*C term of H
+                const float gC = gH * me.x;               // d/dC
+                float2 o2 = make_float2(0.f, normalise ? __fdiv_rn(gv, fy) : gv);
+                *reinterpret_cast<float2*>(grad_kps + (obj * n + kk) * 2) = o2;
+                float* o3 = grad_kps3d + (obj * n + kk) * 3;
+                o3[0] = gC * sn;
+                o3[1] = gH;
+                o3[2] = -gC * cs;
+            }
+        }
+    }
+}
+
+int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+int device_sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot, const float* K,
+                          int64_t N, int n, float lo, float hi, int flags,
+                          float* depth_edges, float* depth_mean, cudaStream_t st) {
+    constexpr int T = 256;
+    const int E = n * (n - 1) / 2;
+    const int64_t max_grid = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(N < max_grid ? N : max_grid);
+    size_t smem = (size_t)2 * n * sizeof(float4) + 2 * (T / 32) * sizeof(float);
+    if (n == 73) {
+        if (depth_edges)
+            edge_solve_fwd_kernel<73, T, true><<<grid, T, smem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags, depth_edges, depth_mean);
+        else
+            edge_solve_fwd_kernel<73, T, false><<<grid, T, smem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags, depth_edges, depth_mean);
+    } else {
+        smem += (size_t)E * sizeof(uint16_t);
+        if (depth_edges) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(edge_solve_fwd_kernel<0, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            edge_solve_fwd_kernel<0, T, true><<<grid, T, smem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags, depth_edges, depth_mean);
+        } else {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(edge_solve_fwd_kernel<0, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            edge_solve_fwd_kernel<0, T, false><<<grid, T, smem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags, depth_edges, depth_mean);
+        }
+    }
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+int launch_edge_select(const float* kps, const float* kps3d, const float* rot, const float* K,
+                       const uint8_t* kpt_mask, int64_t N, int n, int k, float lo, float hi, int flags,
+                       int64_t* idx_out, float* depth_sel, float* mask_sel, float* depth_mean, cudaStream_t st) {
+    constexpr int T = 256;
+    const int E = n * (n - 1) / 2;
+    const int P = next_pow2(E < 2 ? 2 : E);
+    size_t smem = (size_t)P * 4 + (size_t)n * 16 + (T / 32) * 4 + (size_t)P * 2 + (size_t)((n + 15) & ~15);
+    if (smem > 227 * 1024) return DCD_E_UNSUPPORTED;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(edge_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t max_grid = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(N < max_grid ? N : max_grid);
+    edge_select_kernel<T><<<grid, T, smem, st>>>(kps, kps3d, rot, K, kpt_mask, N, n, P, k, lo, hi, flags,
+                                                 idx_out, depth_sel, mask_sel, depth_mean);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+int launch_edge_solve_bwd(const float* kps, const float* kps3d, const float* rot, const float* K,
+                          int64_t N, int n, float lo, float hi, int flags, const int64_t* idx, int k,
+                          const float* grad_depth, const float* grad_mean, float* grad_kps, float* grad_kps3d,
+                          cudaStream_t st) {
+    constexpr int T = 256;
+    const int E = n * (n - 1) / 2;
+    size_t smem = (size_t)n * 16 + (idx != nullptr ? (size_t)E * 4 : 0);
+    if (smem > 227 * 1024) return DCD_E_UNSUPPORTED;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(edge_solve_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t max_grid = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(N < max_grid ? N : max_grid);
+    edge_solve_bwd_kernel<T><<<grid, T, smem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags, idx, k,
+                                                    grad_depth, grad_mean, grad_kps, grad_kps3d);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

@@ -1,0 +1,358 @@
+"""Host-side mirror of the reference's call surface for the densely-constrained-depth path.
+
+Same names, argument meaning and return values as the reference functions they replace
+(SURVEY.md section 8b); the arithmetic runs in libdcd_b200.so (CUDA, sm_100a).  There is no
+CPU path: non-CUDA tensors raise.
+
+    decode_pairs_kpts_depth   <- Anno_Encoder.decode_pairs_kpts_depth   DGDE/model/anno_encoder.py:326
+    compute_z                 <- compute_z                              GMW/main.py:373
+    GMW.forward               <- GMW.forward                            GMW/model/model.py:195
+    compute_reg_loss          <- compute_reg_loss                       GMW/main.py:364
+plus fused fast paths for callers that do not need the per-edge intermediates:
+    edge_depth_mean           decode_pairs_kpts_depth(...)[0].mean(1)   detector_infer.py:222-225, detector_loss.py:388
+    gmw_weighted_depth        compute_z -> GMW.forward -> weighted sum  GMW/main.py:524-533
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+from .weights import NET_DEPTH, NET_NAMES, blob_size, pack_state_dict, unpack_blob
+
+K_SEL = 1500                 # anno_encoder.py:378, GMW/main.py:413
+DGDE_CLAMP = (2.0, 80.0)     # anno_encoder.py:375
+GMW_CLAMP = (0.1, 80.0)      # GMW/main.py:410
+FLAG_NORMALISE_2D = 1
+FLAG_SUB_B3 = 2
+MAX_KPTS = 256
+
+
+def _num_edges(n: int) -> int:
+    return n * (n - 1) // 2
+
+
+def _check_shapes(kps, kps_3d, rot, K=None):
+    if kps.dim() != 3 or kps.shape[-1] != 2:
+        raise ValueError("kps must be [N,n,2], got %s" % (tuple(kps.shape),))
+    N, n = kps.shape[0], kps.shape[1]
+    if tuple(kps_3d.shape) != (N, n, 3):
+        raise ValueError("kps_3d must be [N,n,3] matching kps, got %s" % (tuple(kps_3d.shape),))
+    if rot.numel() != N:
+        raise ValueError("rot_y must hold one yaw per object ([N,1] or [N])")
+    if K is not None and tuple(K.shape) != (N, 3, 4):
+        raise ValueError("K must be [N,3,4], got %s" % (tuple(K.shape),))
+    if not 2 <= n <= MAX_KPTS:
+        raise ValueError("keypoints per object must be in [2, %d]" % MAX_KPTS)
+    return N, n
+
+
+# ---------------------------------------------------------------------------------------------
+# edge solve
+# ---------------------------------------------------------------------------------------------
+class _EdgeSolve(torch.autograd.Function):
+    """All E edge depths (+ optional fused mean).  Gradients flow to kps and kps_3d only."""
+
+    @staticmethod
+    def forward(ctx, kps, kps_3d, rot, K, lo, hi, flags, want_edges, want_mean):
+        N, n = kps.shape[0], kps.shape[1]
+        E = _num_edges(n)
+        dev = kps.device
+        edges = torch.empty((N, E), dtype=torch.float32, device=dev) if want_edges else None
+        mean = torch.empty((N,), dtype=torch.float32, device=dev) if want_mean else None
+        if N:
+            check(_lib.lib().dcd_edge_solve_fwd(ptr(kps), ptr(kps_3d), ptr(rot), ptr(K), N, n, lo, hi, flags,
+                                                ptr(edges), ptr(mean), stream_ptr()), "dcd_edge_solve_fwd")
+        ctx.save_for_backward(kps, kps_3d, rot, K)
+        ctx.cfg = (lo, hi, flags)
+        ctx.set_materialize_grads(False)
+        if edges is None:
+            edges = torch.empty((0,), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(edges)
+        if mean is None:
+            mean = torch.empty((0,), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(mean)
+        return edges, mean
+
+    @staticmethod
+    def backward(ctx, g_edges, g_mean):
+        kps, kps_3d, rot, K = ctx.saved_tensors
+        lo, hi, flags = ctx.cfg
+        N, n = kps.shape[0], kps.shape[1]
+        g_kps = torch.zeros_like(kps)
+        g_k3 = torch.zeros_like(kps_3d)
+        if N and (g_edges is not None or g_mean is not None):
+            ge = f32c(g_edges) if g_edges is not None else None
+            gm = f32c(g_mean) if g_mean is not None else None
+            check(_lib.lib().dcd_edge_solve_bwd(ptr(kps), ptr(kps_3d), ptr(rot), ptr(K), N, n, lo, hi, flags,
+                                                0, 0, ptr(ge), ptr(gm), ptr(g_kps), ptr(g_k3), stream_ptr()),
+                  "dcd_edge_solve_bwd")
+        return g_kps, g_k3, None, None, None, None, None, None, None
+
+
+class _EdgeSelectSolve(torch.autograd.Function):
+    """Top-k edges by |V| (canonical order) with their depths, pair mask and mean."""
+
+    @staticmethod
+    def forward(ctx, kps, kps_3d, rot, K, mask_u8, lo, hi, flags, k, want_mean):
+        N, n = kps.shape[0], kps.shape[1]
+        dev = kps.device
+        idx = torch.empty((N, k), dtype=torch.int64, device=dev)
+        depth = torch.empty((N, k), dtype=torch.float32, device=dev)
+        msel = torch.empty((N, k), dtype=torch.float32, device=dev) if mask_u8 is not None else None
+        mean = torch.empty((N,), dtype=torch.float32, device=dev) if want_mean else None
+        if N:
+            check(_lib.lib().dcd_edge_select_fwd(ptr(kps), ptr(kps_3d), ptr(rot), ptr(K), ptr(mask_u8), N, n, k,
+                                                 lo, hi, flags, ptr(idx), ptr(depth), ptr(msel), ptr(mean),
+                                                 stream_ptr()), "dcd_edge_select_fwd")
+        ctx.save_for_backward(kps, kps_3d, rot, K, idx)
+        ctx.cfg = (lo, hi, flags, k)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(idx)
+        if msel is None:
+            msel = torch.empty((0,), dtype=torch.float32, device=dev)
+        ctx.mark_non_differentiable(msel)
+        if mean is None:
+            mean = torch.empty((0,), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(mean)
+        return depth, msel, idx, mean
+
+    @staticmethod
+    def backward(ctx, g_depth, _g_mask, _g_idx, g_mean):
+        kps, kps_3d, rot, K, idx = ctx.saved_tensors
+        lo, hi, flags, k = ctx.cfg
+        N, n = kps.shape[0], kps.shape[1]
+        g_kps = torch.zeros_like(kps)
+        g_k3 = torch.zeros_like(kps_3d)
+        if N and (g_depth is not None or g_mean is not None):
+            gd = f32c(g_depth) if g_depth is not None else None
+            gm = f32c(g_mean) if g_mean is not None else None
+            check(_lib.lib().dcd_edge_solve_bwd(ptr(kps), ptr(kps_3d), ptr(rot), ptr(K), N, n, lo, hi, flags,
+                                                ptr(idx), k, ptr(gd), ptr(gm), ptr(g_kps), ptr(g_k3), stream_ptr()),
+                  "dcd_edge_solve_bwd")
+        return g_kps, g_k3, None, None, None, None, None, None, None, None
+
+
+def _prep_dgde(kps, kps_3d, rot_y, K):
+    require_cuda(kps, kps_3d, rot_y, K)
+    kps, kps_3d = f32c(kps), f32c(kps_3d)
+    rot = f32c(rot_y).reshape(-1)
+    K = f32c(K)                       # float64 stride-0 calibration at inference (detector_infer.py:221)
+    _check_shapes(kps, kps_3d, rot, K)
+    return kps, kps_3d, rot, K
+
+
+def decode_pairs_kpts_depth(kps, kps_3d, rot_y, K, training=False, kpts_2d_mask=None, gt_depth=None, weight=None,
+                            num_k: int = K_SEL, return_idx: bool = False):
+    """Drop-in for Anno_Encoder.decode_pairs_kpts_depth (DGDE/model/anno_encoder.py:326-390).
+
+    Returns (depth_all, depth_mask): depth_all is [N,E] (all edges, row-major i<j order) when not
+    training, else the [N,1500] depths of the edges with the largest |v_i - v_j| sorted descending
+    (ties by ascending edge id); depth_mask is the float32 0/1 product of the keypoint masks of the
+    selected pairs, or None when kpts_2d_mask is None.  `gt_depth` and `weight` are accepted and
+    unused, as in the reference.  Differentiable w.r.t. kps (v column) and kps_3d.
+    """
+    kps, kps_3d, rot, K = _prep_dgde(kps, kps_3d, rot_y, K)
+    n = kps.shape[1]
+    flags = FLAG_NORMALISE_2D | FLAG_SUB_B3
+    lo, hi = DGDE_CLAMP
+    if not training:
+        depth, _ = _EdgeSolve.apply(kps, kps_3d, rot, K, lo, hi, flags, True, False)
+        mask = None
+        if kpts_2d_mask is not None:   # the reference still returns the (un-gathered) pair mask in this case
+            m = kpts_2d_mask.to(torch.float32)
+            ii, jj = torch.triu_indices(n, n, 1, device=kps.device)
+            mask = m[:, ii] * m[:, jj]
+        return (depth, mask, None) if return_idx else (depth, mask)
+    if _num_edges(n) < num_k:
+        raise RuntimeError("selected index k out of range: %d edges < k=%d (n=%d keypoints)" % (_num_edges(n), num_k, n))
+    mask_u8 = None
+    if kpts_2d_mask is not None:
+        require_cuda(kpts_2d_mask)
+        mask_u8 = (kpts_2d_mask != 0).to(torch.uint8).contiguous()
+    depth, msel, idx, _ = _EdgeSelectSolve.apply(kps, kps_3d, rot, K, mask_u8, lo, hi, flags, num_k, False)
+    mask = msel if kpts_2d_mask is not None else None
+    return (depth, mask, idx) if return_idx else (depth, mask)
+
+
+def edge_depth_mean(kps, kps_3d, rot_y, K, training=False, num_k: int = K_SEL) -> torch.Tensor:
+    """Fused `decode_pairs_kpts_depth(...)[0].mean(1)` (detector_infer.py:222-225, detector_loss.py:388):
+    per-object depth [N] without materialising the per-edge depths."""
+    kps, kps_3d, rot, K = _prep_dgde(kps, kps_3d, rot_y, K)
+    flags = FLAG_NORMALISE_2D | FLAG_SUB_B3
+    lo, hi = DGDE_CLAMP
+    if not training:
+        return _EdgeSolve.apply(kps, kps_3d, rot, K, lo, hi, flags, False, True)[1]
+    if _num_edges(kps.shape[1]) < num_k:
+        raise RuntimeError("selected index k out of range")
+    return _EdgeSelectSolve.apply(kps, kps_3d, rot, K, None, lo, hi, flags, num_k, True)[3]
+
+
+def compute_z(kpts_2d, kpts_3d, pred_rot, num_k: int = K_SEL) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for GMW/main.py:373-416: (Z_v_raw [b,E] clamped to [0.1,80], good_idx [b,1500] int64)."""
+    require_cuda(kpts_2d, kpts_3d, pred_rot)
+    kps, kps_3d = f32c(kpts_2d), f32c(kpts_3d)
+    rot = f32c(pred_rot).reshape(-1)
+    N, n = _check_shapes(kps, kps_3d, rot)
+    if _num_edges(n) < num_k:
+        raise RuntimeError("selected index k out of range")
+    lo, hi = GMW_CLAMP
+    with torch.no_grad():
+        Z, _ = _EdgeSolve.apply(kps, kps_3d, rot, None, lo, hi, 0, True, False)
+        idx = torch.empty((N, num_k), dtype=torch.int64, device=kps.device)
+        if N:
+            check(_lib.lib().dcd_edge_select_fwd(ptr(kps), ptr(kps_3d), ptr(rot), 0, 0, N, n, num_k, lo, hi, 0,
+                                                 ptr(idx), 0, 0, 0, stream_ptr()), "dcd_edge_select_fwd")
+    return Z, idx
+
+
+# ---------------------------------------------------------------------------------------------
+# GMW edge weights + aggregation
+# ---------------------------------------------------------------------------------------------
+def _alloc_bytes(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(((nbytes + 255) // 256 * 64,), dtype=torch.float32, device=dev)
+
+
+class _GmwWeights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kpts_2d, kpts_3d, params4, params6, depth, need_grad):
+        N, n = kpts_2d.shape[0], kpts_2d.shape[1]
+        E = _num_edges(n)
+        dev = kpts_2d.device
+        L = _lib.lib()
+        reg_w = torch.empty((N, E), dtype=torch.float32, device=dev)
+        save = 1 if need_grad else 0
+        ws = None
+        if N:
+            nbytes = L.dcd_gmw_workspace_bytes(N, n, depth, save)
+            ws = _alloc_bytes(nbytes, dev)
+            check(L.dcd_gmw_weights_fwd(ptr(kpts_2d), ptr(kpts_3d), ptr(params4), ptr(params6), N, n, depth, save,
+                                        ptr(reg_w), 0, 0, ptr(ws), ws.numel() * 4, stream_ptr()), "dcd_gmw_weights_fwd")
+        if need_grad:
+            ctx.save_for_backward(kpts_2d, kpts_3d, params4, params6)
+            ctx.ws = ws
+            ctx.depth = depth
+        return reg_w
+
+    @staticmethod
+    def backward(ctx, g_reg_w):
+        kpts_2d, kpts_3d, params4, params6 = ctx.saved_tensors
+        N, n = kpts_2d.shape[0], kpts_2d.shape[1]
+        L = _lib.lib()
+        g4 = torch.zeros_like(params4)
+        g6 = torch.zeros_like(params6)
+        if N:
+            g = f32c(g_reg_w)
+            scratch = _alloc_bytes(L.dcd_gmw_bwd_scratch_bytes(N, n, ctx.depth), g.device)
+            check(L.dcd_gmw_weights_bwd(ptr(kpts_2d), ptr(kpts_3d), ptr(params4), ptr(params6), N, n, ctx.depth,
+                                        ptr(g), ptr(g4), ptr(g6), ptr(ctx.ws), ctx.ws.numel() * 4,
+                                        ptr(scratch), scratch.numel() * 4, stream_ptr()), "dcd_gmw_weights_bwd")
+        ctx.ws = None
+        return None, None, g4, g6, None, None
+
+
+class _GmwAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, reg_w, depths, idx):
+        N, E = reg_w.shape
+        k = idx.shape[1]
+        out = torch.empty((N,), dtype=torch.float32, device=reg_w.device)
+        if N:
+            check(_lib.lib().dcd_gmw_aggregate_fwd(ptr(reg_w), ptr(depths), ptr(idx), N, E, k, 0, ptr(out), 0,
+                                                   stream_ptr()), "dcd_gmw_aggregate_fwd")
+        ctx.save_for_backward(reg_w, depths, idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        reg_w, depths, idx = ctx.saved_tensors
+        N, E = reg_w.shape
+        k = idx.shape[1]
+        g_w = torch.empty_like(reg_w)
+        g_z = torch.empty_like(depths) if ctx.needs_input_grad[1] else None
+        if N:
+            check(_lib.lib().dcd_gmw_aggregate_bwd(ptr(reg_w), ptr(depths), ptr(idx), N, E, k, 0, ptr(f32c(g_out)),
+                                                   ptr(g_w), ptr(g_z), stream_ptr()), "dcd_gmw_aggregate_bwd")
+        return g_w, g_z, None
+
+
+class GMW(nn.Module):
+    """Drop-in for the reference `GMW` module's regression branch (GMW/model/model.py:103-207).
+
+    forward(kpts_2d, kpts_3d, pred_rot, args) -> (reg_weights [b,E], edge_P); `pred_rot` and `args`
+    are ignored as in the reference.  edge_P (the Sinkhorn correspondence matrix
+    of the classification branch) is not computed and returned as None.
+    Parameters live in two flat blobs; `load_state_dict`/`state_dict` of the *reference* format
+    are available through `load_reference_state_dict` / `reference_state_dict`.
+    """
+
+    def __init__(self, args=None, depth: int = NET_DEPTH):
+        super().__init__()
+        self.depth = depth
+        self.params4 = nn.Parameter(torch.zeros(blob_size(4, depth)))
+        self.params6 = nn.Parameter(torch.zeros(blob_size(6, depth)))
+
+    def load_reference_state_dict(self, sd: Dict[str, torch.Tensor]) -> "GMW":
+        sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}   # main.py:286-289
+        with torch.no_grad():
+            for (name, cin), p in zip(NET_NAMES, (self.params4, self.params6)):
+                p.copy_(pack_state_dict(sd, name, cin, self.depth).to(p.device))
+        return self
+
+    def reference_state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for (name, cin), p in zip(NET_NAMES, (self.params4, self.params6)):
+            out.update({k: v.detach().clone() for k, v in unpack_blob(p.data, name, cin, self.depth).items()})
+        return out
+
+    def reference_grads(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for (name, cin), p in zip(NET_NAMES, (self.params4, self.params6)):
+            out.update({k: v.clone() for k, v in unpack_blob(p.grad, name, cin, self.depth).items()})
+        return out
+
+    def forward(self, kpts_2d, kpts_3d, pred_rot=None, args=None):
+        require_cuda(kpts_2d, kpts_3d, self.params4)
+        k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
+        if k2.dim() != 3 or k2.shape[-1] != 2 or tuple(k3.shape) != (k2.shape[0], k2.shape[1], 3):
+            raise ValueError("kpts_2d must be [b,n,2] and kpts_3d [b,n,3]")
+        need_grad = torch.is_grad_enabled() and (self.params4.requires_grad or self.params6.requires_grad)
+        reg_w = _GmwWeights.apply(k2, k3, self.params4, self.params6, self.depth, need_grad)
+        return reg_w, None
+
+
+def compute_reg_loss(pre_depths, edge_weight, gt_depth, good_idx=None):
+    """Drop-in for GMW/main.py:364-371 -> (reg_loss, Z_select_weighted)."""
+    if good_idx is None:
+        raise UnboundLocalError("compute_reg_loss needs good_idx (the reference fails without it too)")
+    require_cuda(pre_depths, edge_weight, good_idx)
+    idx = good_idx.to(torch.int64).contiguous()
+    Z = _GmwAggregate.apply(f32c(edge_weight), f32c(pre_depths), idx)
+    reg_loss = (Z - gt_depth).abs().mean()
+    return reg_loss, Z
+
+
+def gmw_weighted_depth(kpts_2d, kpts_3d, pred_rot, model: GMW, chunk: int = 1024, num_k: int = K_SEL,
+                       return_idx: bool = False):
+    """Fused GMW inference (GMW/main.py:524-533): per-object softmax-weighted depth [b]."""
+    require_cuda(kpts_2d, kpts_3d, pred_rot, model.params4)
+    k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
+    rot = f32c(pred_rot).reshape(-1)
+    N, n = _check_shapes(k2, k3, rot)
+    if _num_edges(n) < num_k:
+        raise RuntimeError("selected index k out of range")
+    L = _lib.lib()
+    out = torch.empty((N,), dtype=torch.float32, device=k2.device)
+    idx = torch.empty((N, num_k), dtype=torch.int64, device=k2.device) if return_idx else None
+    if N:
+        chunk = max(1, min(chunk, N))
+        ws = _alloc_bytes(L.dcd_gmw_depth_workspace_bytes(N, n, model.depth, chunk), k2.device)
+        lo, hi = GMW_CLAMP
+        with torch.no_grad():
+            check(L.dcd_gmw_depth_fwd(ptr(k2), ptr(k3), ptr(rot), ptr(model.params4), ptr(model.params6), N, n,
+                                      model.depth, num_k, lo, hi, chunk, ptr(out), ptr(idx), 0, ptr(ws),
+                                      ws.numel() * 4, stream_ptr()), "dcd_gmw_depth_fwd")
+    return (out, idx) if return_idx else out

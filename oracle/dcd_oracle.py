@@ -1,0 +1,294 @@
+"""ORACLE — CPU restatement of DCD's densely-constrained-depth hot path (TEST INFRASTRUCTURE).
+
+This module is the checker, never the product: only `tests/`, `__graft_entry__.smoke()`
+and the `cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  The
+product (`dcd_b200/`) never imports anything under `oracle/` and has no CPU fallback.
+
+The reference is pure Python/PyTorch, so the restatement is written with the same torch
+elementwise operations in the same order (that is what makes it bit-identical on CPU);
+it is device-agnostic, so GPU tests can also evaluate it with torch-CUDA ops as the
+"reference run on CUDA" of SURVEY.md section 8c.
+
+Parity pin: the reference holds NO golden vectors or tests for this path (SURVEY.md
+section 4), so the oracle is pinned against outputs of the reference itself, produced in
+the build container by `oracle/make_golden.py` (which imports the unmodified reference
+through `oracle/ref_loader.py`) and committed under `tests/golden/`.
+`tests/test_oracle_golden.py` checks every function below against those fixtures.
+
+Reference citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+K_SEL = 1500          # DGDE/model/anno_encoder.py:378, GMW/main.py:413
+CN_EPS = 1e-3         # GMW/model/yi2018cvpr/ops.py:14
+NET_DEPTH = 12        # GMW/model/yi2018cvpr/config.py:69
+NET_CH = 128          # GMW/model/yi2018cvpr/config.py:72
+
+
+# ----------------------------------------------------------------------------------
+# edge enumeration  (anno_encoder.py:313-324, GMW/main.py:351-362, GMW/model/model.py:121-135)
+# ----------------------------------------------------------------------------------
+def edge_pairs(n: int, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row-major strict upper triangle: for i in range(n): for j in range(i+1, n)."""
+    ii, jj = [], []
+    for i in range(n):
+        for j in range(i + 1, n):
+            ii.append(i)
+            jj.append(j)
+    return (torch.tensor(ii, dtype=torch.int64, device=device),
+            torch.tensor(jj, dtype=torch.int64, device=device))
+
+
+def get_up(matrix: torch.Tensor, faithful: bool = False) -> torch.Tensor:
+    """[b,n,n] -> [b,E] strict upper triangle, row-major (anno_encoder.py:313-324).
+
+    faithful=True walks the pairs one column at a time like the reference does (this is
+    what its run time consists of, so the CPU baseline uses it); the default gathers.
+    The reference returns a float32 tensor whatever the input dtype (torch.zeros default);
+    the restatement keeps the input dtype for floating inputs so FP64 evaluation works.
+    """
+    b, n = matrix.shape[0], matrix.shape[1]
+    out_dtype = matrix.dtype if matrix.dtype.is_floating_point else torch.float32
+    if faithful:
+        upper = torch.zeros((b, n * (n - 1) // 2), dtype=out_dtype, device=matrix.device)
+        e = 0
+        for i in range(n):
+            for j in range(i + 1, n):
+                upper[:, e] = matrix[:, i, j]
+                e += 1
+        return upper
+    ii, jj = edge_pairs(n, matrix.device)
+    return matrix[:, ii, jj].to(out_dtype)
+
+
+# ----------------------------------------------------------------------------------
+# edge-depth solve  (anno_encoder.py:326-390 ; GMW/main.py:373-416)
+# ----------------------------------------------------------------------------------
+def _edge_terms(v: torch.Tensor, kps_3d: torch.Tensor, rot: torch.Tensor, faithful: bool):
+    """Shared body: per-edge H, V for normalised vertical coordinate v [N,n].
+
+    anno_encoder.py:339-369 / main.py:379-404: only the odd (v) rows of B and C are used.
+    """
+    X = kps_3d[:, :, 0:1]
+    Y = kps_3d[:, :, 1:2]
+    Z = kps_3d[:, :, 2:3]
+    cosori = torch.cos(rot).unsqueeze(-1).expand_as(X)
+    sinori = torch.sin(rot).unsqueeze(-1).expand_as(X)
+    C = X * sinori - Z * cosori                       # :346-347  (two products, then subtract)
+    H_1 = Y                                           # :345,349
+    H_2 = v.unsqueeze(-1) * C                         # :350-353
+    n = v.shape[1]
+    if faithful:
+        H1_1 = H_1.expand(-1, n, n)
+        H1_2 = H_2.expand(-1, n, n)
+        V1 = v.unsqueeze(-1).expand(-1, n, n)
+        H_mat = (H1_1 - H1_1.permute(0, 2, 1)) + (H1_2 - H1_2.permute(0, 2, 1))   # :367
+        V_mat = V1 - V1.permute(0, 2, 1)                                          # :369
+        Zm = H_mat.abs() / V_mat.abs().clamp_min(1e-10)                           # :371
+        return get_up(Zm, True), get_up(V_mat, True)
+    ii, jj = edge_pairs(n, v.device)
+    y = H_1[:, :, 0]
+    h2 = H_2[:, :, 0]
+    H = (y[:, ii] - y[:, jj]) + (h2[:, ii] - h2[:, jj])
+    V = v[:, ii] - v[:, jj]
+    return H.abs() / V.abs().clamp_min(1e-10), V
+
+
+def normalise_v(kps: torch.Tensor, K: torch.Tensor) -> torch.Tensor:
+    """anno_encoder.py:331-334 (v column only; the u column is dead)."""
+    return (kps[:, :, 1] - K[:, None, 1, 2]) / K[:, None, 1, 1]
+
+
+def canonical_topk(absV: torch.Tensor, k: int) -> torch.Tensor:
+    """Indices of the k largest |V| sorted by (|V| descending, edge id ascending).
+
+    torch.topk (anno_encoder.py:379) breaks ties arbitrarily; this is the canonical rule
+     the CUDA kernel implements bit-exactly.
+    """
+    order = torch.sort(absV, dim=-1, descending=True, stable=True).indices
+    return order[:, :k]
+
+
+def topk_is_canonical_equivalent(absV: torch.Tensor, idx: torch.Tensor, k: int) -> bool:
+    """True when `idx` (e.g. from torch.topk) selects the same keys in the same sorted order as
+    the canonical rule, i.e. differs at most by permutations inside groups of equal keys and by
+    the choice among equal keys at the rank-k boundary."""
+    can = canonical_topk(absV, k)
+    return bool(torch.equal(absV.gather(-1, idx), absV.gather(-1, can)))
+
+
+def decode_pairs_kpts_depth(kps, kps_3d, rot_y, K, training=False, kpts_2d_mask=None,
+                            faithful=False, canonical=True, num_k=K_SEL,
+                            return_idx=False):
+    """DGDE edge solve, anno_encoder.py:326-390.
+
+    kps [N,n,2] pixels, kps_3d [N,n,3], rot_y [N,1], K [N,3,4]; returns (depth_all, depth_mask)
+    exactly like the reference: [N,E] when not training, [N,num_k] (sorted by |V|) when training;
+    depth_mask float32 0/1 or None.  `canonical` selects the tie rule for the top-k.
+    """
+    b3 = K[:, 2, 3]
+    v = normalise_v(kps, K).to(kps.dtype)
+    Zraw, V = _edge_terms(v, kps_3d, rot_y, faithful)
+    Zraw = Zraw.clamp_min(2.).clamp_max(80)                                        # :375
+    depth_mask = None
+    if kpts_2d_mask is not None:
+        m = kpts_2d_mask
+        ii, jj = edge_pairs(m.shape[1], m.device)
+        depth_mask = (m[:, ii] * m[:, jj]).to(torch.float32)                       # :362-365
+    good_idx = None
+    if training:
+        absV = V.abs()
+        good_idx = canonical_topk(absV, num_k) if canonical else torch.topk(absV, num_k, dim=-1)[1]
+        depth_all = Zraw.gather(-1, good_idx)                                      # :380
+        if depth_mask is not None:
+            depth_mask = depth_mask.gather(-1, good_idx)                           # :382
+    else:
+        depth_all = Zraw
+    depth_all = depth_all - b3.unsqueeze(-1).to(depth_all.dtype)                   # :385
+    if return_idx:
+        return depth_all, depth_mask, good_idx
+    return depth_all, depth_mask
+
+
+def compute_z(kpts_2d, kpts_3d, pred_rot, faithful=False, canonical=True, num_k=K_SEL):
+    """GMW edge solve, GMW/main.py:373-416: pre-normalised 2D points, clamp [0.1, 80], no b3."""
+    v = kpts_2d[:, :, 1]
+    Zraw, V = _edge_terms(v, kpts_3d, pred_rot, faithful)
+    Zraw = Zraw.clamp_min(0.1).clamp_max(80.)                                      # :410
+    absV = V.abs()
+    good_idx = canonical_topk(absV, num_k) if canonical else torch.topk(absV, num_k, dim=-1)[1]
+    return Zraw, good_idx
+
+
+def edge_abs_v(v: torch.Tensor) -> torch.Tensor:
+    """|V| keys of every edge for normalised v [N,n] (the top-k ranking key)."""
+    ii, jj = edge_pairs(v.shape[1], v.device)
+    return (v[:, ii] - v[:, jj]).abs()
+
+
+# ----------------------------------------------------------------------------------
+# GMW edge features, edge MLP, weights, aggregation
+# ----------------------------------------------------------------------------------
+def edge_expand(f: torch.Tensor) -> torch.Tensor:
+    """GMW/model/model.py:153-163: [b,n,c] -> [b,E,2c] = concat(kp_i, kp_j) in edge order."""
+    ii, jj = edge_pairs(f.shape[1], f.device)
+    return torch.cat((f[:, ii], f[:, jj]), dim=-1)
+
+
+def context_norm(x: torch.Tensor) -> torch.Tensor:
+    """GMW/model/yi2018cvpr/ops.py:12-19, x [b,C,E]; unbiased variance over the edge axis."""
+    m = torch.mean(x, 2, keepdim=True)
+    v = torch.var(x, 2, keepdim=True)
+    inv = 1. / torch.sqrt(v + CN_EPS)
+    return (x - m) * inv
+
+
+def _conv(x, sd, key):
+    return F.conv1d(x, sd[key + ".0.weight"], sd[key + ".0.bias"])
+
+
+def edge_net(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, depth: int = NET_DEPTH,
+             keep: Optional[list] = None) -> torch.Tensor:
+    """yi2018cvpr/model.py:63-67 + ops.py:125-131, x [b,Cin,E] -> [b,128,E].
+
+    Block = preconv (plain conv) -> conv1 (conv + CN) -> conv2 (conv + CN) -> ReLU -> + input
+    (no BatchNorm anywhere: SURVEY fact 8).  `sd` uses the reference state_dict key names.
+    """
+    x = _conv(x, sd, prefix + ".conv_in")
+    for k in range(depth):
+        xorg = x
+        p = prefix + ".conv_%d" % k
+        x = _conv(x, sd, p + ".preconv")
+        x = context_norm(_conv(x, sd, p + ".conv1"))
+        x = context_norm(_conv(x, sd, p + ".conv2"))
+        x = F.relu(x) + xorg
+        if keep is not None:
+            keep.append(x)
+    return x
+
+
+def edge_distance_diag(f4: torch.Tensor, f6: torch.Tensor) -> torch.Tensor:
+    """Diagonal of pairwiseL2Dist (GMW/model/model.py:28-35) for unit-normalised f4,f6 [b,E,128].
+
+    Same expansion and association as the reference: ((|c|^2) + (-2)(a.c)) + |a|^2, clamp 1e-30, sqrt.
+    """
+    a2 = f4.pow(2).sum(dim=-1)
+    c2 = f6.pow(2).sum(dim=-1)
+    ac = (f4 * f6).sum(dim=-1)
+    return ((c2 + (-2.0) * ac) + a2).clamp_min(1e-30).sqrt()
+
+
+def gmw_reg_weights(kpts_2d, kpts_3d, sd, depth: int = NET_DEPTH, full_matrix: bool = False,
+                    return_feats: bool = False):
+    """GMW.forward's first output (GMW/model/model.py:195-207 -> :170-181): reg_weights [b,E].
+
+    full_matrix=True evaluates the E x E baddbmm like the reference (the only way the reference
+    can reach the diagonal; used for the CPU baseline); otherwise diagonal only.
+    """
+    f4 = edge_expand(kpts_2d)
+    f6 = edge_expand(kpts_3d)
+    f4 = edge_net(f4.transpose(-2, -1), sd, "FeatureExtractor4d", depth).transpose(-2, -1)
+    f6 = edge_net(f6.transpose(-2, -1), sd, "FeatureExtractor6d", depth).transpose(-2, -1)
+    f4 = F.normalize(f4, p=2, dim=-1)
+    f6 = F.normalize(f6, p=2, dim=-1)
+    if full_matrix:
+        x1n = f4.pow(2).sum(dim=-1, keepdim=True)
+        x2n = f6.pow(2).sum(dim=-1, keepdim=True)
+        M = torch.baddbmm(x2n.transpose(-2, -1), f4, f6.transpose(-2, -1), alpha=-2
+                          ).add_(x1n).clamp_min_(1e-30).sqrt_()
+        w = 1. / M.diagonal(offset=0, dim1=-2, dim2=-1)
+    else:
+        w = 1. / edge_distance_diag(f4, f6)
+    if return_feats:
+        return w, f4, f6
+    return w
+
+
+def compute_reg_loss(pre_depths, edge_weight, gt_depth, good_idx):
+    """GMW/main.py:364-371."""
+    z = pre_depths.gather(-1, good_idx)
+    w = edge_weight.gather(-1, good_idx).softmax(dim=-1)
+    Z_select_weighted = (z * w).sum(-1)
+    reg_loss = (Z_select_weighted - gt_depth).abs().mean()
+    return reg_loss, Z_select_weighted
+
+
+def gmw_pipeline(kpts_2d, kpts_3d, pred_rot, sd, depth: int = NET_DEPTH, faithful: bool = False):
+    """Whole GMW forward of GMW/main.py:524-533: compute_z -> GMW.forward -> weighted depth [b]."""
+    with torch.no_grad():
+        Z, idx = compute_z(kpts_2d, kpts_3d, pred_rot, faithful=faithful)
+    w = gmw_reg_weights(kpts_2d, kpts_3d, sd, depth, full_matrix=faithful)
+    z = Z.gather(-1, idx)
+    p = w.gather(-1, idx).softmax(dim=-1)
+    return (z * p).sum(-1)
+
+
+def dgde_pipeline(kps, kps_3d, rot_y, K, faithful: bool = False):
+    """DGDE inference: decode_pairs_kpts_depth(training=False) + mean (detector_infer.py:222-225)."""
+    d, _ = decode_pairs_kpts_depth(kps, kps_3d, rot_y, K, training=False, faithful=faithful)
+    return d.mean(1)
+
+
+def random_state_dict(seed: int, depth: int = NET_DEPTH, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Seeded weights with torch's Conv1d default init bounds and the reference's key names
+    (used on the GPU box, where the reference module cannot be instantiated)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, cin):
+        bound = 1.0 / math.sqrt(cin)
+        sd[key + ".0.weight"] = ((torch.rand((NET_CH, cin, 1), generator=g) * 2 - 1) * bound).to(dtype)
+        sd[key + ".0.bias"] = ((torch.rand((NET_CH,), generator=g) * 2 - 1) * bound).to(dtype)
+
+    for name, cin in (("FeatureExtractor4d", 4), ("FeatureExtractor6d", 6)):
+        conv(name + ".conv_in", cin)
+        for k in range(depth):
+            for sub in ("preconv", "conv1", "conv2"):
+                conv("%s.conv_%d.%s" % (name, k, sub), NET_CH)
+    return sd

@@ -1,0 +1,179 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden            # from the repo root
+
+For every fixture the script (1) runs the reference functions imported through
+oracle/ref_loader.py on seeded synthetic inputs, (2) asserts that oracle/dcd_oracle.py
+reproduces them (bit-exactly on CPU wherever the operation sequence is deterministic), and
+(3) stores inputs + reference outputs.  The fixtures pin the oracle; the GPU parity tests
+compare the CUDA path with the oracle and with these stored reference outputs.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import dcd_oracle as O      # noqa: E402
+from oracle import ref_loader as rl     # noqa: E402
+from dcd_b200 import synth              # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def inputs_dict(ob):
+    return dict(kps=npy(ob.kps), kps_norm=npy(ob.kps_norm), kps_3d=npy(ob.kps_3d), rot_y=npy(ob.rot_y),
+                K=npy(ob.K), mask=npy(ob.mask), gt_depth=npy(ob.gt_depth))
+
+
+def dgde_fixture(name, N, n, seed, with_grad=True):
+    enc = rl.load_dgde_anno_encoder()
+    ob = synth.make_objects(N=N, n=n, seed=seed)
+    out = inputs_dict(ob)
+    report = {}
+    t0 = time.time()
+    d_inf, none = enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+    report["t_ref_infer_s"] = time.time() - t0
+    assert none is None
+    d_or, _ = O.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+    assert torch.equal(d_inf, d_or), "oracle != reference (infer)"
+    # inference call with the float64 stride-0 K of detector_infer.py:221
+    K64 = ob.K[0].double().unsqueeze(0).expand(N, -1, -1) if n == 73 and N <= 50 else ob.K.double()
+    d64, _ = enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, K64)
+    out["infer_depth_mean"] = npy(d_inf.mean(1))
+    out["infer_f64K_equal"] = np.array(bool(torch.equal(d64, d_inf)) if K64.shape == ob.K.shape and torch.equal(K64.float(), ob.K) else False)
+    if n <= 73:
+        out["infer_depth"] = npy(d_inf)
+    # FP64 evaluation of the same formula (conditioning reference)
+    d_f64, _ = O.decode_pairs_kpts_depth(ob.kps.double(), ob.kps_3d.double(), ob.rot_y.double(), ob.K.double())
+    out["infer_depth_mean_f64"] = npy(d_f64.mean(1))
+    E = n * (n - 1) // 2
+    if E >= O.K_SEL:
+        t0 = time.time()
+        d_tr, m_tr = enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K, training=True, kpts_2d_mask=ob.mask)
+        report["t_ref_train_s"] = time.time() - t0
+        d_o, m_o, idx_t = O.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K, training=True,
+                                                    kpts_2d_mask=ob.mask, canonical=False, return_idx=True)
+        assert torch.equal(d_tr, d_o) and torch.equal(m_tr, m_o), "oracle != reference (train)"
+        assert m_tr.dtype == torch.float32
+        d_c, m_c, idx_c = O.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K, training=True,
+                                                    kpts_2d_mask=ob.mask, canonical=True, return_idx=True)
+        absV = O.edge_abs_v(O.normalise_v(ob.kps, ob.K))
+        assert O.topk_is_canonical_equivalent(absV, idx_t, O.K_SEL)
+        out.update(train_depth_ref=npy(d_tr), train_mask_ref=npy(m_tr), train_idx_ref=npy(idx_t),
+                   train_depth=npy(d_c), train_mask=npy(m_c), train_idx=npy(idx_c),
+                   train_ties=np.array(int((idx_t != idx_c).sum())))
+        same_set = all(set(a.tolist()) == set(b.tolist()) for a, b in zip(idx_t, idx_c))
+        out["train_same_set"] = np.array(same_set)
+        if with_grad:
+            g = torch.Generator().manual_seed(seed + 99)
+            G_edge = torch.randn(N, E, generator=g)
+            kps = ob.kps.clone().requires_grad_(True)
+            k3 = ob.kps_3d.clone().requires_grad_(True)
+            t0 = time.time()
+            d_g, m_g = enc.decode_pairs_kpts_depth(kps, k3, ob.rot_y, ob.K, training=True, kpts_2d_mask=ob.mask)
+            (d_g * G_edge.gather(-1, idx_t)).sum().backward()
+            report["t_ref_train_fwd_bwd_s"] = time.time() - t0
+            kps_o = ob.kps.clone().requires_grad_(True)
+            k3_o = ob.kps_3d.clone().requires_grad_(True)
+            d_go, _, idx_go = O.decode_pairs_kpts_depth(kps_o, k3_o, ob.rot_y, ob.K, training=True,
+                                                        kpts_2d_mask=ob.mask, canonical=True, return_idx=True)
+            (d_go * G_edge.gather(-1, idx_go)).sum().backward()
+            if same_set:
+                for a, b in ((kps.grad, kps_o.grad), (k3.grad, k3_o.grad)):
+                    assert (a - b).abs().max() <= 1e-4 * a.abs().max(), "oracle grad != reference grad"
+            assert float(kps.grad[:, :, 0].abs().max()) == 0.0      # u-gradient is exactly 0
+            out.update(G_edge=npy(G_edge), grad_kps=npy(kps.grad), grad_kps_3d=npy(k3.grad))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: round(v, 3) for k, v in report.items()}, "ties", out.get("train_ties"))
+
+
+def gmw_fixture(name, N, seed, wseed):
+    main, _ = rl.load_gmw()
+    ob = synth.make_objects(N=N, n=73, seed=seed)
+    sd = O.random_state_dict(wseed)
+    model = rl.new_gmw_model(0)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    out = inputs_dict(ob)
+    out["weight_seed"] = np.array(wseed)
+    with torch.no_grad():
+        Z_ref, idx_ref = main.compute_z(ob.kps_norm, ob.kps_3d, ob.rot_y)
+    Z_o, idx_t = O.compute_z(ob.kps_norm, ob.kps_3d, ob.rot_y, canonical=False)
+    assert torch.equal(Z_ref, Z_o) and torch.equal(idx_ref, idx_t)
+    _, idx_c = O.compute_z(ob.kps_norm, ob.kps_3d, ob.rot_y, canonical=True)
+    absV = O.edge_abs_v(ob.kps_norm[:, :, 1])
+    assert O.topk_is_canonical_equivalent(absV, idx_ref, O.K_SEL)
+    # edge_expand parity
+    model_ee4 = model.edge_expand(ob.kps_norm)
+    assert torch.equal(model_ee4, O.edge_expand(ob.kps_norm))
+    assert torch.equal(model.edge_expand(ob.kps_3d), O.edge_expand(ob.kps_3d))
+    t0 = time.time()
+    w_ref, _P = model(ob.kps_norm, ob.kps_3d, ob.rot_y, None)       # full forward incl. E x E + Sinkhorn
+    t_fwd = time.time() - t0
+    loss_ref, zsel_ref = main.compute_reg_loss(Z_ref, w_ref, ob.gt_depth, idx_c)
+    model.zero_grad()
+    t0 = time.time()
+    loss_ref.backward()
+    t_bwd = time.time() - t0
+    names = [k for k, _ in model.named_parameters()]
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    # oracle parity (full-matrix form is bit-identical, diagonal form within FP32 noise)
+    with torch.no_grad():
+        w_full = O.gmw_reg_weights(ob.kps_norm, ob.kps_3d, sd, full_matrix=True)
+        w_diag, f4, f6 = O.gmw_reg_weights(ob.kps_norm, ob.kps_3d, sd, return_feats=True)
+    assert torch.equal(w_full, w_ref.detach()), "oracle(full) != reference GMW.forward"
+    rel = ((w_diag - w_ref).abs() / w_ref.abs()).max().item()
+    assert rel < 2e-5, rel
+    _, zsel_o = O.compute_reg_loss(Z_ref, w_diag, ob.gt_depth, idx_c)
+    assert ((zsel_o - zsel_ref).abs() / zsel_ref.abs()).max() < 1e-6
+    # oracle gradient parity through the diagonal form
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    w_g = O.gmw_reg_weights(ob.kps_norm, ob.kps_3d, sd_g)
+    l_g, _ = O.compute_reg_loss(Z_ref, w_g, ob.gt_depth, idx_c)
+    l_g.backward()
+    worst = 0.0
+    for k in names:
+        a, b = grads[k], sd_g[k].grad
+        worst = max(worst, float((a - b).abs().max() / max(float(a.abs().max()), 1e-12)) if a.abs().max() > 1e-6 else 0.0)
+    flat = torch.cat([grads[k].reshape(-1) for k in names])
+    # FP64 evaluation (conditioning reference)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        w64 = O.gmw_reg_weights(ob.kps_norm.double(), ob.kps_3d.double(), sd64)
+        _, zsel64 = O.compute_reg_loss(Z_ref.double(), w64, ob.gt_depth.double(), idx_c)
+    out.update(Z=npy(Z_ref), idx_ref=npy(idx_ref), idx=npy(idx_c), reg_weights=npy(w_ref), reg_weights_f64=npy(w64),
+               z_select_weighted=npy(zsel_ref), z_select_weighted_f64=npy(zsel64), reg_loss=npy(loss_ref),
+               feat4_sample=npy(f4[:, ::97, :]), feat6_sample=npy(f6[:, ::97, :]),
+               grad_names=np.array(names), grad_sample=npy(flat[::61]),
+               grad_norms=np.array([float(grads[k].norm()) for k in names], dtype=np.float64),
+               grad_absmax=np.array([float(grads[k].abs().max()) for k in names], dtype=np.float64),
+               grad_conv_in4_w=npy(grads["FeatureExtractor4d.conv_in.0.weight"]),
+               grad_conv_in6_w=npy(grads["FeatureExtractor6d.conv_in.0.weight"]),
+               grad_last4_w=npy(grads["FeatureExtractor4d.conv_11.conv2.0.weight"]),
+               grad_first6_w=npy(grads["FeatureExtractor6d.conv_0.preconv.0.weight"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ref fwd %.2fs bwd %.2fs" % (t_fwd, t_bwd), "diag-vs-full rel", rel, "oracle grad worst rel", worst)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    dgde_fixture("dgde_n73_N10", N=10, n=73, seed=synth.BASE_SEED)          # BASELINE configs[0]
+    dgde_fixture("dgde_n73_N64", N=64, n=73, seed=synth.BASE_SEED + 10, with_grad=False)
+    dgde_fixture("dgde_n60_N5", N=5, n=60, seed=synth.BASE_SEED + 11)
+    dgde_fixture("dgde_n8_N7", N=7, n=8, seed=synth.BASE_SEED + 12)         # E=28 < 1500: inference only
+    dgde_fixture("dgde_n256_N4", N=4, n=256, seed=synth.BASE_SEED + 4)      # BASELINE configs[4]
+    gmw_fixture("gmw_n73_N4", N=4, seed=synth.BASE_SEED + 3, wseed=7)
+
+
+if __name__ == "__main__":
+    main()

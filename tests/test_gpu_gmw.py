@@ -1,0 +1,203 @@
+"""GPU parity of the GMW edge-weight MLP, aggregation and their backward (through the C ABI).
+
+Forward bars: reg_weights within FP32 accumulation noise of the reference (the reference's own FP32
+result differs from an FP64 evaluation by ~2e-5 relative), per-object weighted depth rel <= 1e-5.
+Gradient bar: rel <= 1e-4 of the tensor's max — asserted on configurations whose ReLU inputs keep a
+margin from zero (the weight gradient is a heavily cancelling sum: a single ReLU whose input sits
+within rounding noise of 0 flips and moves a row of the gradient by ~1 %, which is what the
+reference's own FP32-vs-FP64 comparison shows too; see DESIGN.md "gradient conditioning").
+"""
+import pytest
+import torch
+
+import dcd_b200
+from dcd_b200 import synth
+from dcd_b200.weights import pack_state_dict, unpack_blob
+from oracle import dcd_oracle as O
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(*ts):
+    return [t.to(DEV) if torch.is_tensor(t) else t for t in ts]
+
+
+def make_model(sd, depth=12):
+    return dcd_b200.GMW(depth=depth).to(DEV).load_reference_state_dict(sd)
+
+
+def test_reg_weights_and_depth_vs_reference_fixture(golden):
+    G = golden("gmw_n73_N4")
+    sd = O.random_state_dict(int(G["weight_seed"]))
+    model = make_model(sd)
+    k2, k3, rot, gt = cu(G["kps_norm"], G["kps_3d"], G["rot_y"], G["gt_depth"])
+    with torch.no_grad():
+        w, P = model(k2, k3, rot, None)
+    assert P is None and w.shape == (4, 2628)
+    assert rel_err(w.cpu(), G["reg_weights"]) < 1e-4
+    assert rel_err(w.cpu(), G["reg_weights_f64"]) < 2e-4
+    Z, idx = dcd_b200.compute_z(k2, k3, rot)
+    loss, zsel = dcd_b200.compute_reg_loss(Z, w, gt, idx)
+    assert rel_err(zsel.cpu(), G["z_select_weighted"]) < 1e-5
+    assert rel_err(zsel.cpu(), G["z_select_weighted_f64"]) < 1e-5
+    assert abs(float(loss) - float(G["reg_loss"])) < 1e-5 * float(G["gt_depth"].mean())
+    # fused pipeline
+    fused, idx2 = dcd_b200.gmw_weighted_depth(k2, k3, rot, model, chunk=3, return_idx=True)
+    assert torch.equal(idx2, idx)
+    assert rel_err(fused, zsel) < 1e-6
+
+
+def test_reg_weights_vs_cuda_oracle_small_shapes():
+    """n != 73, shallow nets, partial last tile (E % 128 != 0) and E < 128."""
+    for n, depth, N in ((9, 1, 3), (20, 2, 2), (73, 2, 2), (40, 3, 1)):
+        ob = synth.make_objects(N=N, n=n, seed=100 + n)
+        sd = O.random_state_dict(n, depth=depth)
+        model = make_model(sd, depth)
+        k2, k3 = cu(ob.kps_norm, ob.kps_3d)
+        with torch.no_grad():
+            w, _ = model(k2, k3)
+            w_o = O.gmw_reg_weights(k2, k3, {k: v.to(DEV) for k, v in sd.items()}, depth)
+            w_64 = O.gmw_reg_weights(ob.kps_norm.double(), ob.kps_3d.double(), {k: v.double() for k, v in sd.items()}, depth)
+        assert rel_err(w, w_o) < 1e-4, (n, depth)
+        assert rel_err(w.cpu(), w_64) < 2e-4, (n, depth)
+
+
+def test_aggregate_forward_backward_vs_oracle():
+    g = torch.Generator().manual_seed(2)
+    N, E, k = 5, 2628, 1500
+    w = (1.5 + torch.rand(N, E, generator=g)).to(DEV).requires_grad_(True)
+    z = (5 + 50 * torch.rand(N, E, generator=g)).to(DEV).requires_grad_(True)
+    idx = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(N)]).to(DEV)
+    gt = (5 + 50 * torch.rand(N, generator=g)).to(DEV)
+    loss, Z = dcd_b200.compute_reg_loss(z, w, gt, idx)
+    loss.backward()
+    wo = w.detach().clone().requires_grad_(True)
+    zo = z.detach().clone().requires_grad_(True)
+    loss_o, Zo = O.compute_reg_loss(zo, wo, gt, idx)
+    loss_o.backward()
+    assert rel_err(Z, Zo) < 1e-6
+    for a, b in ((w.grad, wo.grad), (z.grad, zo.grad)):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
+    with pytest.raises(UnboundLocalError):
+        dcd_b200.compute_reg_loss(z, w, gt, None)
+
+
+def _oracle_grads(k2, k3, rot, gt, sd, depth, num_k, dtype, dev):
+    sdg = {k: v.to(device=dev, dtype=dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    Z, idx = O.compute_z(k2.to(dev), k3.to(dev), rot.to(dev), num_k=num_k)
+    keep4 = []
+    w = O.gmw_reg_weights(k2.to(device=dev, dtype=dtype), k3.to(device=dev, dtype=dtype), sdg, depth)
+    loss, _ = O.compute_reg_loss(Z.to(dtype), w, gt.to(device=dev, dtype=dtype), idx)
+    loss.backward()
+    return {k: v.grad for k, v in sdg.items()}, float(loss)
+
+
+def _relu_margin(k2, k3, sd, depth):
+    """Smallest |input| of any ReLU in the two nets (FP64 oracle): gradient parity is only
+    well-posed when this is far above FP32 rounding noise."""
+    sd64 = {k: v.double() for k, v in sd.items()}
+    worst = 1e9
+    for name, f in (("FeatureExtractor4d", O.edge_expand(k2.double())), ("FeatureExtractor6d", O.edge_expand(k3.double()))):
+        x = O._conv(f.transpose(-2, -1), sd64, name + ".conv_in")
+        for b in range(depth):
+            p = name + ".conv_%d" % b
+            y = O._conv(x, sd64, p + ".preconv")
+            y = O.context_norm(O._conv(y, sd64, p + ".conv1"))
+            y = O.context_norm(O._conv(y, sd64, p + ".conv2"))
+            worst = min(worst, float(y.abs().min()))
+            x = torch.relu(y) + x
+    return worst
+
+
+@pytest.mark.parametrize("n,depth,N,num_k", [(12, 2, 3, 40), (20, 1, 2, 100), (16, 3, 2, 64)])
+def test_weight_gradients_small_well_posed(n, depth, N, num_k):
+    # pick the first seed whose ReLU inputs keep a margin (deterministic: the search is seeded)
+    for seed in range(200, 260):
+        ob = synth.make_objects(N=N, n=n, seed=seed)
+        sd = O.random_state_dict(seed, depth=depth)
+        if _relu_margin(ob.kps_norm, ob.kps_3d, sd, depth) > 2e-5:
+            break
+    else:
+        pytest.skip("no seed with a ReLU margin found")
+    model = make_model(sd, depth)
+    k2, k3, rot, gt = cu(ob.kps_norm, ob.kps_3d, ob.rot_y, ob.gt_depth)
+    Z, idx = dcd_b200.compute_z(k2, k3, rot, num_k=num_k)
+    w, _ = model(k2, k3, rot, None)
+    loss, _ = dcd_b200.compute_reg_loss(Z, w, gt, idx)
+    loss.backward()
+    mine = model.reference_grads()
+    ref64, loss64 = _oracle_grads(ob.kps_norm, ob.kps_3d, ob.rot_y, ob.gt_depth, sd, depth, num_k, torch.float64, "cpu")
+    ref32, _ = _oracle_grads(ob.kps_norm, ob.kps_3d, ob.rot_y, ob.gt_depth, sd, depth, num_k, torch.float32, DEV)
+    assert abs(float(loss) - loss64) < 1e-5 * float(ob.gt_depth.mean())
+    gmax = max(float(v.abs().max()) for v in ref64.values())
+    for key, g64 in ref64.items():
+        tol = 1e-4 * max(float(g64.abs().max()), 1e-3 * gmax)     # dead biases: |g| ~ 0
+        assert float((mine[key].cpu().double() - g64).abs().max()) <= tol, key
+        assert float((mine[key] - ref32[key]).abs().max()) <= 2 * tol, key
+
+
+def test_weight_gradients_full_size_vs_reference_fixture(golden):
+    """n=73, depth 12, the reference's own FP32 gradients (fixture).  Conditioning-limited: asserted
+    with the tolerance the reference's FP32-vs-FP64 self-comparison supports (see module docstring)."""
+    G = golden("gmw_n73_N4")
+    sd = O.random_state_dict(int(G["weight_seed"]))
+    model = make_model(sd)
+    k2, k3, rot, gt = cu(G["kps_norm"], G["kps_3d"], G["rot_y"], G["gt_depth"])
+    Z, idx = dcd_b200.compute_z(k2, k3, rot)
+    w, _ = model(k2, k3, rot, None)
+    loss, _ = dcd_b200.compute_reg_loss(Z, w, gt, idx)
+    loss.backward()
+    mine = model.reference_grads()
+    names = [str(s) for s in G["grad_names"]]
+    flat = torch.cat([mine[k].reshape(-1) for k in names]).cpu()
+    sample = flat[::61]
+    ref = G["grad_sample"]
+    cos = float((sample * ref).sum() / (sample.norm() * ref.norm()))
+    assert cos > 0.999, cos
+    norms = torch.tensor([float(mine[k].norm()) for k in names], dtype=torch.float64)
+    big = G["grad_norms"] > 1e-4 * G["grad_norms"].max()
+    assert float(((norms - G["grad_norms"]).abs() / G["grad_norms"].clamp_min(1e-30))[big].max()) < 5e-2
+    for key, fix in (("FeatureExtractor4d.conv_in.0.weight", "grad_conv_in4_w"),
+                     ("FeatureExtractor6d.conv_in.0.weight", "grad_conv_in6_w"),
+                     ("FeatureExtractor4d.conv_11.conv2.0.weight", "grad_last4_w"),
+                     ("FeatureExtractor6d.conv_0.preconv.0.weight", "grad_first6_w")):
+        a, b = mine[key].cpu(), G[fix]
+        assert float((a - b).abs().max()) <= 5e-2 * float(b.abs().max()), key
+    # dead parameters: block biases are cancelled by the following mean subtraction
+    gmax = float(G["grad_absmax"].max())
+    for k in names:
+        if ".conv_" in k and k.endswith("bias") and "conv_in" not in k:
+            assert float(mine[k].abs().max()) < 1e-4 * gmax, k
+
+
+def test_state_dict_round_trip():
+    sd = O.random_state_dict(3)
+    model = make_model(sd)
+    back = model.reference_state_dict()
+    assert set(back) == set(sd)
+    for k in sd:
+        assert torch.equal(back[k].cpu(), sd[k]) and back[k].shape == sd[k].shape
+
+
+def test_full_size_properties_gmw():
+    """Slice of BASELINE configs[1]: fused pipeline == staged pipeline, chunking invariance, softmax bounds."""
+    ob = synth.kitti_val_batch(ragged=True, frames=6)
+    sd = O.random_state_dict(9)
+    model = make_model(sd)
+    k2, k3, rot = cu(ob.kps_norm, ob.kps_3d, ob.rot_y)
+    a = dcd_b200.gmw_weighted_depth(k2, k3, rot, model, chunk=1024)
+    b = dcd_b200.gmw_weighted_depth(k2, k3, rot, model, chunk=17)
+    assert torch.equal(a, b)
+    Z, idx = dcd_b200.compute_z(k2, k3, rot)
+    zsel = Z.gather(-1, idx)
+    assert bool((a >= zsel.min(1).values - 1e-4).all()) and bool((a <= zsel.max(1).values + 1e-4).all())
+    with torch.no_grad():
+        w, _ = model(k2, k3)
+    _, staged = dcd_b200.compute_reg_loss(Z, w, ob.gt_depth.to(DEV), idx)
+    assert rel_err(a, staged) < 1e-6
+    # oracle on a few objects (CPU, the reference's E x E form is too slow for more)
+    with torch.no_grad():
+        ref = O.gmw_pipeline(ob.kps_norm[:3], ob.kps_3d[:3], ob.rot_y[:3], sd)
+    assert rel_err(a[:3].cpu(), ref) < 1e-5
