@@ -55,7 +55,7 @@ def golden():
 
 
 def rel_err(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())
 
 

@@ -133,7 +133,8 @@ def test_weight_gradients_small_well_posed(n, depth, N, num_k):
     assert abs(float(loss) - loss64) < 1e-5 * float(ob.gt_depth.mean())
     gmax = max(float(v.abs().max()) for v in ref64.values())
     for key, g64 in ref64.items():
-        tol = 1e-4 * max(float(g64.abs().max()), 1e-3 * gmax)     # dead biases: |g| ~ 0
+        dead = ".conv_in." not in key and key.endswith("bias")   # cancelled by the mean subtraction: g == 0 exactly
+        tol = 1e-4 * (gmax if dead else float(g64.abs().max()))   # (the reference emits ~1e-7 noise there)
         assert float((mine[key].cpu().double() - g64).abs().max()) <= tol, key
         assert float((mine[key] - ref32[key]).abs().max()) <= 2 * tol, key
 
