@@ -16,6 +16,7 @@ int launch_gmw_aggregate_bwd(const float*, const float*, const int64_t*, int64_t
 int launch_gmw_weights_fwd(const float*, const float*, const float*, const float*, int64_t, int, int, int, float*,
                            float*, float*, float*, cudaStream_t);
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
+size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
                            float*, float*, float*, float*, cudaStream_t);
 }  // namespace dcd
@@ -89,7 +90,8 @@ size_t dcd_gmw_param_count(int cin, int depth) { return (size_t)blob_size(cin, d
 
 size_t dcd_gmw_workspace_bytes(int64_t N, int n, int depth, int save) {
     if (N <= 0 || bad_n(n) || depth < 1) return 0;
-    return (size_t)make_layout(N, n, depth, save).total * sizeof(float);
+    // activations + context-norm statistics, then the FP16 hi/lo tensor-core image of the weights
+    return align_up((size_t)make_layout(N, n, depth, save).total * sizeof(float), 256) + tc_weight_image_bytes(depth);
 }
 
 int dcd_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
