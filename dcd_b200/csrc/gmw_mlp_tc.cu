@@ -33,32 +33,27 @@ namespace {
 
 enum { MODE_FIRST = 0, MODE_B = 1, MODE_CA = 2 };
 
-// ---- tensor-core weight image: [net][blk][which]{ hi[128*128] half, lo[128*128] half }, + unscale floats
-constexpr int W_HALFS = CH * CH;                       // 16384 halfs = 32 KB per part
-constexpr size_t W_PART_BYTES = (size_t)W_HALFS * 2;   // 32768
-constexpr uint32_t A_LBO = 128, A_SBO = 2048;          // K-major: K-core stride, M-block stride (bytes)
-constexpr uint32_t B_SBO = 128, B_LBO = 2048;          // MN-major: N-block stride, K-block stride (bytes)
-constexpr uint32_t A_KSTEP = 2 * A_LBO;                // 16 k-elements = 2 K-cores
-constexpr uint32_t B_KSTEP = 2 * B_LBO;
-constexpr int TC_THREADS = 256;
-constexpr int TMEM_COLS = 128;
+// ---- operand geometry
+constexpr size_t B_PART_BYTES = (size_t)CH * TE * 2;   // 32 KB: one FP16 part (hi or lo) of a [128 k][128 edge] operand
+constexpr uint32_t B_SBO = 128, B_LBO = 2048;          // MN-major no-swizzle: N-block stride, K-block stride (bytes)
+constexpr uint32_t B_KSTEP = 2 * B_LBO;                // one MMA consumes K = 16 = 2 K-blocks
+constexpr int TC_THREADS = 256;                        // two groups of 4 warps, each with its own tile stream
+constexpr int GROUP_THREADS = 128;
+// tensor memory map (512 columns): resident weights as the A operand, one accumulator per group
+constexpr uint32_t TM_W0_HI = 0, TM_W0_LO = 64, TM_W1_HI = 128, TM_W1_LO = 192, TM_D0 = 256, TM_D1 = 384;
+constexpr uint32_t TMEM_COLS = 512;
 
 // smem carve (bytes)
-constexpr size_t SM_A = 0;                                   // 4 x 32 KB: W(a) hi, lo, W(b) hi, lo
-constexpr size_t SM_B = SM_A + 4 * W_PART_BYTES;             // 2 x 32 KB: X hi, lo
-constexpr size_t SM_STAT = SM_B + 2 * W_PART_BYTES;          // 128 float2
-constexpr size_t SM_F = SM_STAT + CH * sizeof(float2);       // 128 x 8 floats edge features (FIRST)
-constexpr size_t SM_HALF = SM_F + TE * 8 * sizeof(float);    // 128 x float4 half-tile statistics exchange
-constexpr size_t SM_BAR = SM_HALF + CH * sizeof(float4);     // mbarriers + tmem pointer
+constexpr size_t SM_B = 0;                                       // [group]{hi, lo} : 4 x 32 KB
+constexpr size_t SM_STAT = SM_B + 4 * B_PART_BYTES;              // [group][128] float2
+constexpr size_t SM_F = SM_STAT + 2 * CH * sizeof(float2);       // [group][128 edges][8] floats (FIRST)
+constexpr size_t SM_BAR = SM_F + 2 * TE * 8 * sizeof(float);     // mbarriers + tmem pointer
 constexpr size_t kTcSmem = SM_BAR + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -71,15 +66,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GROUP_THREADS) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
@@ -91,14 +85,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem], FP16 inputs, FP32 accumulate, M = 128, N = 128, K = 16
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem], FP16 inputs, FP32 accumulate, M = 128, N = 128, K = 16
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // 32 lanes x 32 columns of FP32 accumulators -> 32 registers per thread (thread = TMEM lane)
@@ -118,15 +112,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: version 1, layout_type 0)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = F32, A = B = F16, A K-major, B MN-major, N = 128, M = 128
+// instruction descriptor: D = F32, A = B = F16, A K-major (TMEM), B MN-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 16) | ((uint32_t)(TE >> 3) << 17) | ((uint32_t)(CH >> 4) << 24);
 
-// One 128x128x128 layer GEMM as 3 x 8 MMAs: Wh.Xl, Wl.Xh, Wh.Xh  (issued by one thread)
+// One 128x128x128 layer GEMM as 3 x 8 MMAs: Wh.Xl, Wl.Xh, Wh.Xh  (issued by one thread).
+// A lives in tensor memory (K = 16 halfs = 8 columns per step), B in shared memory.
 __device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
     uint32_t acc = 0;
 #pragma unroll
@@ -135,7 +141,7 @@ __device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, uint32_t a_hi,
         const uint32_t b = (term == 0) ? b_lo : b_hi;
 #pragma unroll
         for (int ks = 0; ks < CH / 16; ++ks) {
-            umma_f16(tmem_d, smem_desc(a + ks * A_KSTEP, A_LBO, A_SBO), smem_desc(b + ks * B_KSTEP, B_LBO, B_SBO), kIdesc, acc);
+            umma_f16_ts(tmem_d, a + ks * 8, smem_desc(b + ks * B_KSTEP, B_LBO, B_SBO), kIdesc, acc);
             acc = 1;
         }
     }
@@ -155,94 +161,115 @@ __device__ __forceinline__ void store_b8(unsigned char* b_hi, unsigned char* b_l
     *reinterpret_cast<uint4*>(b_lo + off) = *reinterpret_cast<const uint4*>(l);
 }
 
-__global__ void __launch_bounds__(256) tc_prep_weights_kernel(const float* __restrict__ p4, const float* __restrict__ p6,
-                                                              int depth, __half* __restrict__ wimg, float* __restrict__ unscale) {
+// per-matrix power-of-two scale that puts max|W| in [512, 1024): FP16 hi/lo both stay normal
+__global__ void __launch_bounds__(256) tc_weight_scales_kernel(const float* __restrict__ p4, const float* __restrict__ p6,
+                                                               int depth, float2* __restrict__ scales) {
     const int m = blockIdx.x;                               // (net, blk, which)
     const int which = m % 3, blk = (m / 3) % depth, net = m / (3 * depth);
     const int cin = net == 0 ? 4 : 6;
-    const float* Wt = (net == 0 ? p4 : p6) + blob_w(cin, blk, which);     // [in k][out m]
+    const float* Wt = (net == 0 ? p4 : p6) + blob_w(cin, blk, which);
     __shared__ float red[8];
     float mx = 0.f;
     for (int i = threadIdx.x; i < CH * CH; i += 256) mx = fmaxf(mx, fabsf(Wt[i]));
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
-    mx = 0.f;
-    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
-    int e = 0;
-    if (mx > 0.f) frexpf(mx, &e);                           // mx = f * 2^e, f in [0.5, 1)
-    const float scale = ldexpf(1.f, 10 - e);                // scaled max in [512, 1024)
-    if (threadIdx.x == 0) unscale[m] = ldexpf(1.f, e - 10);
-    __half* hi = wimg + (size_t)m * 2 * W_HALFS;
-    __half* lo = hi + W_HALFS;
-    for (int i = threadIdx.x; i < CH * CH; i += 256) {
-        const int k = i >> 7, mo = i & 127;                 // coalesced read of Wt[k][mo]
-        const float w = Wt[i] * scale;
-        const __half h = __float2half_rn(w);
-        const int off = ((mo >> 3) * (int)A_SBO + (k >> 3) * (int)A_LBO + (mo & 7) * 16 + (k & 7) * 2) >> 1;
-        hi[off] = h;
-        lo[off] = __float2half_rn(w - __half2float(h));
+    if (threadIdx.x == 0) {
+        mx = 0.f;
+        for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        int e = 0;
+        if (mx > 0.f) frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+        scales[m] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
     }
+}
+
+// One output-channel row of a weight matrix -> FP16 hi/lo pairs -> tensor memory (A operand, K-major:
+// lane = out channel, 32-bit column c holds input channels 2c (low half) and 2c+1).
+__device__ __forceinline__ void load_weight_row_to_tmem(const float* __restrict__ Wt, float scale, int row,
+                                                        uint32_t t_hi, uint32_t t_lo) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int k = half * 64 + 2 * c;
+            const float w0 = __ldg(Wt + (int64_t)k * CH + row) * scale;
+            const float w1 = __ldg(Wt + (int64_t)(k + 1) * CH + row) * scale;
+            const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
+            const __half l0 = __float2half_rn(w0 - __half2float(h0)), l1 = __float2half_rn(w1 - __half2float(h1));
+            hi[c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        tmem_st32(t_hi + half * 32, hi);
+        tmem_st32(t_lo + half * 32, lo);
+    }
+    tc_wait_st();
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-mlp_tc_kernel(MlpArgs a, int blk, const __half* __restrict__ wimg, const float* __restrict__ unscale) {
+mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const WsLayout& L = a.L;
     const int net = blockIdx.y;
     const int cin = net == 0 ? 4 : 6;
     const float* __restrict__ prm = a.params[net];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = warp >> 2, gwarp = warp & 3, gtid = tid & (GROUP_THREADS - 1);
     const int E = L.E, EP = L.EP, T = L.T;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* A0_hi = smem + SM_A;
-    unsigned char* A0_lo = A0_hi + W_PART_BYTES;
-    unsigned char* A1_hi = A0_lo + W_PART_BYTES;
-    unsigned char* A1_lo = A1_hi + W_PART_BYTES;
-    unsigned char* B_hi = smem + SM_B;
-    unsigned char* B_lo = B_hi + W_PART_BYTES;
-    float2* stat_s = reinterpret_cast<float2*>(smem + SM_STAT);
-    float* f_s = reinterpret_cast<float*>(smem + SM_F);
-    float4* half_s = reinterpret_cast<float4*>(smem + SM_HALF);
-    uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    uint64_t* bar_mma = bar_w + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_w + 2);
+    unsigned char* B_hi = smem + SM_B + (size_t)group * 2 * B_PART_BYTES;
+    unsigned char* B_lo = B_hi + B_PART_BYTES;
+    float2* stat_s = reinterpret_cast<float2*>(smem + SM_STAT) + group * CH;
+    float* f_s = reinterpret_cast<float*>(smem + SM_F) + group * TE * 8;
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + SM_BAR) + group;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);
 
-    // ---- one-time setup: barriers, TMEM, resident weights
+    // ---- one-time setup: barriers, tensor memory, resident weights
     const int w0 = (MODE == MODE_B) ? 2 : 0;                // first matrix of this segment (conv2 | preconv)
     const int mat0 = (net * L.depth + blk) * 3 + w0;
     if (tid == 0) {
-        mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(smem + SM_BAR), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(smem + SM_BAR) + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr;
-    if (tid == 0) {
-        const uint32_t bytes = (MODE == MODE_B ? 2u : 4u) * (uint32_t)W_PART_BYTES;
-        mbar_expect_tx(bar_w, bytes);
-        bulk_g2s(A0_hi, wimg + (size_t)mat0 * 2 * W_HALFS, 2 * W_PART_BYTES, bar_w);
-        if (MODE != MODE_B) bulk_g2s(A1_hi, wimg + (size_t)(mat0 + 1) * 2 * W_HALFS, 2 * W_PART_BYTES, bar_w);
+    const uint32_t tmem_base = *tmem_ptr;
+    const int ch = 32 * gwarp + lane;                       // this thread's TMEM lane = output channel
+    const uint32_t lane_off = (uint32_t)(32 * gwarp) << 16;
+    const float2 sc0 = __ldg(scales + mat0);
+    const float2 sc1 = (MODE != MODE_B) ? __ldg(scales + mat0 + 1) : make_float2(0.f, 0.f);
+    if (MODE == MODE_B) {
+        if (group == 0)
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 2), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO);
+    } else {
+        if (group == 0)
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 0), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO);
+        else
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 1), sc1.x, ch, tmem_base + lane_off + TM_W1_HI, tmem_base + lane_off + TM_W1_LO);
     }
-    const float un0 = __ldg(unscale + mat0);
-    const float un1 = (MODE != MODE_B) ? __ldg(unscale + mat0 + 1) : 0.f;
-    // epilogue ownership: thread = output channel `ch`, column half `hsel` (64 edges)
-    const int ch = 32 * (warp & 3) + lane;
-    const int hsel = warp >> 2;
-    const uint32_t t_lane = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(hsel * 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tmem_d = tmem_base + (group == 0 ? TM_D0 : TM_D1);
+    const uint32_t t_lane = tmem_d + lane_off;
+    const float un0 = sc0.y, un1 = sc1.y;
     const float bias0 = __ldg(prm + blob_b(cin, blk, w0) + ch);
     const float bias1 = (MODE != MODE_B) ? __ldg(prm + blob_b(cin, blk, 1) + ch) : 0.f;
 
-    uint32_t mma_phase = 0;
-    bool weights_ready = false;
-    int64_t stat_obj = -1;
+    // contiguous tile range of this (CTA, group): consecutive tiles share the object's statistics
     const int64_t ntiles = L.N * (int64_t)T;
+    const int64_t nworkers = (int64_t)gridDim.x * 2;
+    const int64_t wid = (int64_t)blockIdx.x * 2 + group;
+    const int64_t t_begin = ntiles * wid / nworkers, t_end = ntiles * (wid + 1) / nworkers;
 
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint32_t mma_phase = 0;
+    int64_t stat_obj = -1;
+    for (int64_t t = t_begin; t < t_end; ++t) {
         const int64_t obj = t / T;
         const int tile = (int)(t - obj * T);
         const int64_t obj_off = obj * (int64_t)CH * EP;
@@ -250,11 +277,11 @@ mlp_tc_kernel(MlpArgs a, int blk, const __half* __restrict__ wimg, const float* 
 
         // ---- source tile -> B operand (hi/lo)
         if (MODE == MODE_FIRST) {
-            if (tid < TE) {
-                const int e = tile * TE + tid;
+            {
+                const int e = tile * TE + gtid;
                 int i, j;
                 decode_edge(e < E ? e : E - 1, L.n, i, j);
-                float* f = f_s + tid * 8;
+                float* f = f_s + gtid * 8;
                 if (net == 0) {
                     const float2 pi = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + i) * 2));
                     const float2 pj = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + j) * 2));
@@ -266,14 +293,12 @@ mlp_tc_kernel(MlpArgs a, int blk, const __half* __restrict__ wimg, const float* 
                     f[3] = __ldg(pj); f[4] = __ldg(pj + 1); f[5] = __ldg(pj + 2);
                 }
             }
-            __syncthreads();
+            group_sync(group);
         } else if (stat_obj != obj) {
             const int pb = (MODE == MODE_B) ? blk : blk - 1;
             const int which = (MODE == MODE_B) ? 0 : 1;
-            __syncthreads();                                  // previous tile's readers of stat_s are done
-            if (tid < CH)
-                stat_s[tid] = merge_cn_stats(stat_ptr(a.ws, L, net, pb, which) + obj * (int64_t)T * CH, tid, T, E);
-            __syncthreads();
+            stat_s[gtid] = merge_cn_stats(stat_ptr(a.ws, L, net, pb, which) + obj * (int64_t)T * CH, gtid, T, E);
+            group_sync(group);
             stat_obj = obj;
         }
         {
@@ -282,74 +307,86 @@ mlp_tc_kernel(MlpArgs a, int blk, const __half* __restrict__ wimg, const float* 
             const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + obj_off : nullptr;
             float* Xn = (MODE == MODE_B) ? nullptr : act_ptr(a.ws, L, net, MODE == MODE_FIRST ? 0 : blk, SLOT_X) + obj_off;
             const int c_sub = lane & 7, j_sub = lane >> 3;
-#pragma unroll 2
-            for (int it = 0; it < 8; ++it) {
-                const int item = warp * 8 + it;              // 64 items: 16 channel groups x 4 quads of edge blocks
-                const int c = (item >> 2) * 8 + c_sub;
-                const int eblk = (item & 3) * 4 + j_sub;     // block of 8 edges
-                const int e0 = tile * TE + eblk * 8;
-                float v[8];
-                if (MODE == MODE_FIRST) {
-                    const float b = __ldg(prm + blob_in_b(cin) + c);
-                    float wq[6];
+            constexpr int UNR = (MODE == MODE_CA) ? 4 : 8;
+#pragma unroll 1
+            for (int it0 = 0; it0 < 16; it0 += UNR) {
+                float4 ybuf[UNR][2], xbuf[UNR][2];
+                if (MODE != MODE_FIRST) {
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + c) : 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float* f = f_s + (eblk * 8 + q) * 8;
-                        float x = b;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) x = fmaf(wq[r], f[r], x);
-                        v[q] = x;
-                    }
-                } else {
-                    const float2 st = stat_s[c];
-                    const float4 y0 = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0);
-                    const float4 y1 = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0 + 4);
-                    const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
-                    if (MODE == MODE_CA) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0);
-                        const float4 x1 = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0 + 4);
-                        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
+                    for (int u = 0; u < UNR; ++u) {         // all loads of the batch in flight before any use
+                        const int item = gwarp * 16 + it0 + u;
+                        const int c = (item >> 2) * 8 + c_sub;
+                        const int e0 = tile * TE + ((item & 3) * 4 + j_sub) * 8;
+                        ybuf[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0);
+                        ybuf[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0 + 4);
+                        if (MODE == MODE_CA) {
+                            xbuf[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0);
+                            xbuf[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0 + 4);
+                        }
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (eblk * 8 + q >= valid) v[q] = 0.f;
-                if (MODE != MODE_B) {
-                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                for (int u = 0; u < UNR; ++u) {
+                    const int item = gwarp * 16 + it0 + u;  // 64 items: 16 channel groups x 4 quads of edge blocks
+                    const int c = (item >> 2) * 8 + c_sub;
+                    const int eblk = (item & 3) * 4 + j_sub;
+                    const int e0 = tile * TE + eblk * 8;
+                    float v[8];
+                    if (MODE == MODE_FIRST) {
+                        const float b = __ldg(prm + blob_in_b(cin) + c);
+                        float wq[6];
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + c) : 0.f;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float* f = f_s + (eblk * 8 + q) * 8;
+                            float x = b;
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) x = fmaf(wq[r], f[r], x);
+                            v[q] = x;
+                        }
+                    } else {
+                        const float2 st = stat_s[c];
+                        const float yv[8] = {ybuf[u][0].x, ybuf[u][0].y, ybuf[u][0].z, ybuf[u][0].w,
+                                             ybuf[u][1].x, ybuf[u][1].y, ybuf[u][1].z, ybuf[u][1].w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
+                        if (MODE == MODE_CA) {
+                            const float xv[8] = {xbuf[u][0].x, xbuf[u][0].y, xbuf[u][0].z, xbuf[u][0].w,
+                                                 xbuf[u][1].x, xbuf[u][1].y, xbuf[u][1].z, xbuf[u][1].w};
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (eblk * 8 + q >= valid) v[q] = 0.f;
+                    if (MODE != MODE_B) {
+                        *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                    store_b8(B_hi, B_lo, c, eblk, v);
                 }
-                store_b8(B_hi, B_lo, c, eblk, v);
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (!weights_ready) {
-            mbar_wait(bar_w, 0);
-            weights_ready = true;
-        }
+        group_sync(group);
         // ---- GEMM 1
-        if (tid == 0) {
+        if (gtid == 0) {
             tc_fence_after();
-            issue_layer_gemm(tmem_d, smem_u32(A0_hi), smem_u32(A0_lo), smem_u32(B_hi), smem_u32(B_lo));
+            issue_layer_gemm(tmem_d, tmem_base + TM_W0_HI, tmem_base + TM_W0_LO, smem_u32(B_hi), smem_u32(B_lo));
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
 
-        float vals[64];
         if (MODE != MODE_B) {
             // preconv output: + bias, kept on chip as the operand of conv1
-            float* Pg = L.save ? act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off + (int64_t)ch * EP + tile * TE + hsel * 64 : nullptr;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
+            float* Pg = L.save ? act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off + (int64_t)ch * EP + tile * TE : nullptr;
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
                 float v[32];
                 tmem_ld32(t_lane + part * 32, v);
 #pragma unroll
@@ -363,70 +400,66 @@ mlp_tc_kernel(MlpArgs a, int blk, const __half* __restrict__ wimg, const float* 
                 for (int bq = 0; bq < 4; ++bq) {
                     const float w8[8] = {v[bq * 8], v[bq * 8 + 1], v[bq * 8 + 2], v[bq * 8 + 3],
                                          v[bq * 8 + 4], v[bq * 8 + 5], v[bq * 8 + 6], v[bq * 8 + 7]};
-                    store_b8(B_hi, B_lo, ch, hsel * 8 + part * 4 + bq, w8);
+                    store_b8(B_hi, B_lo, ch, part * 4 + bq, w8);
                 }
             }
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            group_sync(group);
             // ---- GEMM 2 (conv1)
-            if (tid == 0) {
+            if (gtid == 0) {
                 tc_fence_after();
-                issue_layer_gemm(tmem_d, smem_u32(A1_hi), smem_u32(A1_lo), smem_u32(B_hi), smem_u32(B_lo));
+                issue_layer_gemm(tmem_d, tmem_base + TM_W1_HI, tmem_base + TM_W1_LO, smem_u32(B_hi), smem_u32(B_lo));
                 umma_commit(bar_mma);
             }
             mbar_wait(bar_mma, mma_phase);
             mma_phase ^= 1;
             tc_fence_after();
         }
-        // ---- final epilogue of the segment: + bias, store, tile statistics
+        // ---- final epilogue of the segment: + bias, store, tile statistics (thread = channel, all 128 edges)
         {
             const float un = (MODE == MODE_B) ? un0 : un1;
             const float bias = (MODE == MODE_B) ? bias0 : bias1;
-            float* Yo = act_ptr(a.ws, L, net, blk, MODE == MODE_B ? SLOT_Y2 : SLOT_Y1) + obj_off + (int64_t)ch * EP + tile * TE + hsel * 64;
-            const int nv = max(0, min(64, valid - hsel * 64));
-            float s = 0.f;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
+            float* Yo = act_ptr(a.ws, L, net, blk, MODE == MODE_B ? SLOT_Y2 : SLOT_Y1) + obj_off + (int64_t)ch * EP + tile * TE;
+            float mean = 0.f, M2 = 0.f, cnt = 0.f;
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
                 float v[32];
                 tmem_ld32(t_lane + part * 32, v);
+                const int nv = max(0, min(32, valid - part * 32));
+                float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     v[i] = fmaf(v[i], un, bias);
-                    vals[part * 32 + i] = v[i];
-                    if (part * 32 + i < nv) s += v[i];
+                    if (i < nv) s += v[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<float4*>(Yo + part * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-            const float mean_h = nv > 0 ? s / (float)nv : 0.f;
-            float m2 = 0.f;
+                if (nv > 0) {
+                    const float pm = s / (float)nv;
+                    float pm2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-                if (i < nv) {
-                    const float d = vals[i] - mean_h;
-                    m2 = fmaf(d, d, m2);
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nv) {
+                            const float d = v[i] - pm;
+                            pm2 = fmaf(d, d, pm2);
+                        }
+                    const float nb = (float)nv, tot = cnt + nb;       // Chan merge of the 32-edge parts
+                    const float delta = pm - mean;
+                    mean += delta * (nb / tot);
+                    M2 += pm2 + delta * delta * (cnt * nb / tot);
+                    cnt = tot;
                 }
-            if (hsel == 1) half_s[ch] = make_float4(mean_h, m2, (float)nv, 0.f);
-            tc_fence_before();
-            __syncthreads();                                  // also orders the TMEM reads before the next tile's MMAs
-            if (hsel == 0) {
-                const float4 o = half_s[ch];
-                float mean = mean_h, M2 = m2;
-                if (o.z > 0.f) {                              // Chan merge of the two 64-edge halves
-                    const float na = (float)nv, nb = o.z, tot = na + nb;
-                    const float delta = o.x - mean_h;
-                    mean = mean_h + delta * (nb / tot);
-                    M2 = m2 + o.y + delta * delta * (na * nb / tot);
-                }
-                stat_ptr(a.ws, L, net, blk, MODE == MODE_B ? 1 : 0)[(obj * T + tile) * (int64_t)CH + ch] = make_float2(mean, M2);
             }
+            stat_ptr(a.ws, L, net, blk, MODE == MODE_B ? 1 : 0)[(obj * T + tile) * (int64_t)CH + ch] = make_float2(mean, M2);
+            tc_fence_before();
+            group_sync(group);                                // TMEM reads done before the next tile's MMAs overwrite D
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // Final features of both nets -> reg_weights (same arithmetic as the CUDA-core path's kernel).
@@ -480,10 +513,9 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
 
 }  // namespace
 
-// bytes appended to the MLP workspace for the tensor-core weight image
+// bytes appended to the MLP workspace for the per-matrix FP16 scales (scale, 1/scale)
 size_t tc_weight_image_bytes(int depth) {
-    const size_t mats = (size_t)2 * depth * 3;
-    return mats * 2 * W_PART_BYTES + ((mats * sizeof(float) + 255) / 256) * 256;
+    return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256;
 }
 
 int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
@@ -495,21 +527,21 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     a.ws = ws;
     a.L = make_layout(N, n, depth, save);
     if ((int64_t)a.L.T * N > 0x7fffffffLL) return DCD_E_UNSUPPORTED;
-    // weight image lives right after the layout's own area (256-byte aligned)
-    unsigned char* img = reinterpret_cast<unsigned char*>(ws) + (((size_t)a.L.total * sizeof(float) + 255) / 256) * 256;
-    __half* wimg = reinterpret_cast<__half*>(img);
-    float* unscale = reinterpret_cast<float*>(img + (size_t)2 * depth * 3 * 2 * W_PART_BYTES);
-    tc_prep_weights_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, wimg, unscale);
+    // the scales live right after the layout's own area (256-byte aligned)
+    float2* scales = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ws) +
+                                               (((size_t)a.L.total * sizeof(float) + 255) / 256) * 256);
+    tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     const int64_t ntiles = a.L.T * N;
     const int per_net = max(1, device_sm_count() / 2);
-    const dim3 grid((unsigned)(ntiles < per_net ? ntiles : per_net), 2);
-    mlp_tc_kernel<MODE_FIRST><<<grid, TC_THREADS, kTcSmem, st>>>(a, 0, wimg, unscale);
+    const int64_t want = (ntiles + 1) / 2;                  // two tile streams (groups) per CTA
+    const dim3 grid((unsigned)(want < per_net ? want : per_net), 2);
+    mlp_tc_kernel<MODE_FIRST><<<grid, TC_THREADS, kTcSmem, st>>>(a, 0, scales);
     for (int blk = 0; blk < depth; ++blk) {
-        mlp_tc_kernel<MODE_B><<<grid, TC_THREADS, kTcSmem, st>>>(a, blk, wimg, unscale);
-        if (blk + 1 < depth) mlp_tc_kernel<MODE_CA><<<grid, TC_THREADS, kTcSmem, st>>>(a, blk + 1, wimg, unscale);
+        mlp_tc_kernel<MODE_B><<<grid, TC_THREADS, kTcSmem, st>>>(a, blk, scales);
+        if (blk + 1 < depth) mlp_tc_kernel<MODE_CA><<<grid, TC_THREADS, kTcSmem, st>>>(a, blk + 1, scales);
     }
     DCD_CHECK_LAUNCH();
     const unsigned g2 = (unsigned)(((a.L.E + 255) / 256) * N);
