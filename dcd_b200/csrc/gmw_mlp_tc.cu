@@ -416,11 +416,14 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             mma_phase ^= 1;
             tc_fence_after();
         }
-        // ---- final epilogue of the segment: + bias, store, tile statistics (thread = channel, all 128 edges)
+        // ---- final epilogue of the segment: + bias, tile statistics (thread = channel, all 128 edges), then a
+        //      coalesced store: the FP32 tile is staged in this group's (now idle) operand buffer, one 512-byte
+        //      row per channel with the 16-byte slots XOR-swizzled by the row so that both the row-owner writes
+        //      and the row-wise reads are bank-conflict free.
         {
             const float un = (MODE == MODE_B) ? un0 : un1;
             const float bias = (MODE == MODE_B) ? bias0 : bias1;
-            float* Yo = act_ptr(a.ws, L, net, blk, MODE == MODE_B ? SLOT_Y2 : SLOT_Y1) + obj_off + (int64_t)ch * EP + tile * TE;
+            float4* stage = reinterpret_cast<float4*>(B_hi);            // [128 rows][32 slots] = 64 KB (B_hi + B_lo)
             float mean = 0.f, M2 = 0.f, cnt = 0.f;
 #pragma unroll 1
             for (int part = 0; part < 4; ++part) {
@@ -434,8 +437,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     if (i < nv) s += v[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(Yo + part * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int q = 0; q < 8; ++q)
+                    stage[ch * 32 + ((part * 8 + q) ^ (ch & 31))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 if (nv > 0) {
                     const float pm = s / (float)nv;
                     float pm2 = 0.f;
@@ -454,7 +457,15 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             }
             stat_ptr(a.ws, L, net, blk, MODE == MODE_B ? 1 : 0)[(obj * T + tile) * (int64_t)CH + ch] = make_float2(mean, M2);
             tc_fence_before();
-            group_sync(group);                                // TMEM reads done before the next tile's MMAs overwrite D
+            group_sync(group);                                // staging complete; TMEM reads done
+            float* Yo = act_ptr(a.ws, L, net, blk, MODE == MODE_B ? SLOT_Y2 : SLOT_Y1) + obj_off + tile * TE;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int r = gwarp * 32 + i;
+                const float4 val = stage[r * 32 + (lane ^ (r & 31))];
+                *reinterpret_cast<float4*>(Yo + (int64_t)r * EP + lane * 4) = val;
+            }
+            group_sync(group);                                // staging buffer free for the next tile's operand
         }
     }
     tc_fence_before();
