@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dcd_b200", choices=["dcd_b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: the KITTI val split)")
-    ap.add_argument("--chunk", type=int, default=1024, help="objects per MLP workspace chunk")
+    ap.add_argument("--chunk", type=int, default=2048, help="objects per MLP workspace chunk")
     ap.add_argument("--cpu-sample", type=int, default=32, help="objects of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -362,11 +362,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": N * 4,
                     "api": "dcd_b200.gmw_weighted_depth on pinned host tensors"},
             "gpu_launches": timed_launches,
-            "roofline": {"kernel": "mlp_fwd_kernel (edge-feature MLP, 36 GEMM layers x 2 nets)", "bound": "tensor",
+            "roofline": {"kernel": "mlp_tc_kernel<FIRST|B|CA> (edge-feature MLP: 36 GEMM layers x 2 nets on tcgen05, FP16x3 split, "
+                                   "FP32 accumulate in TMEM)", "bound": "tensor",
                          "achieved": mlp_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": mlp_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "peak_source": "%s dense bf16 (sustained); this kernel computes in FP32 on the CUDA cores, "
-                                        "FP32-pipe peak %.1f TFLOP/s -> frac_fp32 %.3f" % (peaks["source"], fp32_peak, mlp_tflops / fp32_peak),
+                         "peak_source": "%s dense bf16 (sustained, of measured); `achieved` counts the algorithmic FP32 GEMM FLOPs, the "
+                                        "tensor pipe executes 3 FP16 MMAs per FP32 product (x3 = %.1f TFLOP/s issued); vs the FP32 "
+                                        "CUDA-core roofline (%.1f TFLOP/s) the same number is %.2fx" % (
+                                            peaks["source"], 3 * mlp_tflops, fp32_peak, mlp_tflops / fp32_peak),
+                         "hbm_gbs": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9, "frac_hbm": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "hbm_bytes_per_object": 198.0e6,
                          "flops_per_object": F_MLP, "avg_launch_ms": mlp_ms / max(n_mlp_launches, 1),
                          "share_of_step": mlp_ms_max / ms},
             "stages": {
