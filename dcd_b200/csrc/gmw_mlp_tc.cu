@@ -7,9 +7,10 @@
 // bits) and three MMAs per product:  D = Wh.Xl + Wl.Xh + Wh.Xh   (the dropped Wl.Xl term is 2^-22).
 // Weights are pre-scaled per matrix by a power of two so that hi/lo stay in FP16's normal range; the
 // epilogue multiplies by the exact inverse.  No tensor maps are needed:
-//   * A (weights) is pre-split and pre-tiled in global memory in the canonical K-major no-swizzle UMMA
-//     layout by a prep kernel and lands in shared memory with cp.async.bulk; it stays resident while a
-//     persistent CTA loops over its tiles (one CTA per SM: 74 per net);
+//   * A (weights) is converted once per CTA (FP32 row -> scaled FP16 hi/lo pairs) and stays RESIDENT IN
+//     TENSOR MEMORY as the A operand while the persistent CTA loops over its tiles (one CTA per SM,
+//     74 per net).  With A in shared memory an M = N = 128 MMA would need all 128 B/clk of shared-memory
+//     bandwidth; from tensor memory only B is fetched;
 //   * B (activations) is written straight into the canonical MN-major no-swizzle layout by the threads
 //     that produce it (thread = input channel, 16-byte stores of 8 edges: conflict free), both for the
 //     tile source (context norm + ReLU + residual fused into the load) and for the chained preconv

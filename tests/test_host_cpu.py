@@ -49,8 +49,8 @@ def test_version_strerror_and_size_queries(lib):
     assert lib.dcd_gmw_param_count(4, 12) + lib.dcd_gmw_param_count(6, 12) == 1190400
     E, T = 2628, 21
     acts_and_stats = 4 * (2 * 3 * 128 * T * 128 + 2 * 12 * 2 * T * 128 * 2)
-    weight_image = 2 * 12 * 3 * 2 * 32768 + 512          # FP16 hi/lo tensor-core image + per-matrix scales
-    assert lib.dcd_gmw_workspace_bytes(1, 73, 12, 0) == acts_and_stats + weight_image
+    scales = 768                                         # 72 per-matrix (scale, 1/scale) pairs, 256-byte aligned
+    assert lib.dcd_gmw_workspace_bytes(1, 73, 12, 0) == acts_and_stats + scales
     assert lib.dcd_gmw_workspace_bytes(0, 73, 12, 0) == 0
     assert lib.dcd_gmw_workspace_bytes(8, 73, 12, 1) > lib.dcd_gmw_workspace_bytes(8, 73, 12, 0)
     assert lib.dcd_gmw_bwd_scratch_bytes(8, 73, 12) > 0
