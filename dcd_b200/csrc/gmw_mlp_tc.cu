@@ -270,6 +270,33 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 
     uint32_t mma_phase = 0;
     int64_t stat_obj = -1;
+    // Source-tile prefetch: the first PRE of this thread's 16 items (8 channels x 8 edges each) of the NEXT tile
+    // are loaded into registers right after the current tile's operand is handed to the tensor core, so that
+    // their HBM latency is covered by the MMA waits and both epilogues.
+    constexpr int PRE = (MODE == MODE_FIRST) ? 0 : ((MODE == MODE_CA) ? 8 : 16);
+    float4 ypre[PRE > 0 ? PRE : 1][2], xpre[(MODE == MODE_CA) ? PRE : 1][2];
+    const int c_sub = lane & 7, j_sub = lane >> 3;
+    auto prefetch = [&](int64_t tt) {
+        if (PRE == 0) return;
+        const int64_t o = tt / T;
+        const int tl = (int)(tt - o * T);
+        const int pb = (MODE == MODE_B) ? blk : blk - 1;
+        const float* Y = act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + o * (int64_t)CH * EP;
+        const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + o * (int64_t)CH * EP : nullptr;
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+            const int item = gwarp * 16 + u;
+            const int c = (item >> 2) * 8 + c_sub;
+            const int e0 = tl * TE + ((item & 3) * 4 + j_sub) * 8;
+            ypre[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0);
+            ypre[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0 + 4);
+            if (MODE == MODE_CA) {
+                xpre[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0);
+                xpre[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0 + 4);
+            }
+        }
+    };
+    if (t_begin < t_end) prefetch(t_begin);
     for (int64_t t = t_begin; t < t_end; ++t) {
         const int64_t obj = t / T;
         const int tile = (int)(t - obj * T);
@@ -307,14 +334,56 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             const float* Y = (MODE == MODE_FIRST) ? nullptr : act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + obj_off;
             const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + obj_off : nullptr;
             float* Xn = (MODE == MODE_B) ? nullptr : act_ptr(a.ws, L, net, MODE == MODE_FIRST ? 0 : blk, SLOT_X) + obj_off;
-            const int c_sub = lane & 7, j_sub = lane >> 3;
             constexpr int UNR = (MODE == MODE_CA) ? 4 : 8;
+            const bool full_tile = valid == TE;
+            // convert 8 edges of channel c and store them as FP16 hi/lo into the operand
+            auto convert = [&](int item, const float4& ya, const float4& yb, const float4& xa, const float4& xb) {
+                const int c = (item >> 2) * 8 + c_sub;      // 64 items: 16 channel groups x 4 quads of edge blocks
+                const int eblk = (item & 3) * 4 + j_sub;
+                const int e0 = tile * TE + eblk * 8;
+                float v[8];
+                if (MODE == MODE_FIRST) {
+                    const float b = __ldg(prm + blob_in_b(cin) + c);
+                    float wq[6];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + c) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float* f = f_s + (eblk * 8 + q) * 8;
+                        float x = b;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) x = fmaf(wq[r], f[r], x);
+                        v[q] = x;
+                    }
+                } else {
+                    const float2 st = stat_s[c];
+                    const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
+                    if (MODE == MODE_CA) {
+                        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
+                    }
+                }
+                if (!full_tile) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (eblk * 8 + q >= valid) v[q] = 0.f;
+                }
+                if (MODE != MODE_B) {
+                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                store_b8(B_hi, B_lo, c, eblk, v);
+            };
+            // items loaded here (not covered by the prefetch) first, so their loads overlap the conversion below
+            float4 ybuf[UNR][2], xbuf[UNR][2];
 #pragma unroll 1
-            for (int it0 = 0; it0 < 16; it0 += UNR) {
-                float4 ybuf[UNR][2], xbuf[UNR][2];
+            for (int it0 = PRE; it0 < 16; it0 += UNR) {
                 if (MODE != MODE_FIRST) {
 #pragma unroll
-                    for (int u = 0; u < UNR; ++u) {         // all loads of the batch in flight before any use
+                    for (int u = 0; u < UNR; ++u) {
                         const int item = gwarp * 16 + it0 + u;
                         const int c = (item >> 2) * 8 + c_sub;
                         const int e0 = tile * TE + ((item & 3) * 4 + j_sub) * 8;
@@ -326,48 +395,19 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                         }
                     }
                 }
+                if (it0 == PRE) {                            // prefetched items are converted while those loads fly
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int item = gwarp * 16 + it0 + u;  // 64 items: 16 channel groups x 4 quads of edge blocks
-                    const int c = (item >> 2) * 8 + c_sub;
-                    const int eblk = (item & 3) * 4 + j_sub;
-                    const int e0 = tile * TE + eblk * 8;
-                    float v[8];
-                    if (MODE == MODE_FIRST) {
-                        const float b = __ldg(prm + blob_in_b(cin) + c);
-                        float wq[6];
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + c) : 0.f;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float* f = f_s + (eblk * 8 + q) * 8;
-                            float x = b;
-#pragma unroll
-                            for (int r = 0; r < 6; ++r) x = fmaf(wq[r], f[r], x);
-                            v[q] = x;
-                        }
-                    } else {
-                        const float2 st = stat_s[c];
-                        const float yv[8] = {ybuf[u][0].x, ybuf[u][0].y, ybuf[u][0].z, ybuf[u][0].w,
-                                             ybuf[u][1].x, ybuf[u][1].y, ybuf[u][1].z, ybuf[u][1].w};
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
-                        if (MODE == MODE_CA) {
-                            const float xv[8] = {xbuf[u][0].x, xbuf[u][0].y, xbuf[u][0].z, xbuf[u][0].w,
-                                                 xbuf[u][1].x, xbuf[u][1].y, xbuf[u][1].z, xbuf[u][1].w};
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (eblk * 8 + q >= valid) v[q] = 0.f;
-                    if (MODE != MODE_B) {
-                        *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    }
-                    store_b8(B_hi, B_lo, c, eblk, v);
+                    for (int u = 0; u < PRE; ++u)
+                        convert(gwarp * 16 + u, ypre[u][0], ypre[u][1], xpre[MODE == MODE_CA ? u : 0][0], xpre[MODE == MODE_CA ? u : 0][1]);
                 }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+                    convert(gwarp * 16 + it0 + u, ybuf[u][0], ybuf[u][1], xbuf[u][0], xbuf[u][1]);
+            }
+            if (PRE == 16) {                                 // everything came from the prefetch
+#pragma unroll
+                for (int u = 0; u < PRE; ++u)
+                    convert(gwarp * 16 + u, ypre[u][0], ypre[u][1], xpre[0][0], xpre[0][1]);
             }
         }
         fence_async_smem();
@@ -379,6 +419,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             issue_layer_gemm(tmem_d, tmem_base + TM_W0_HI, tmem_base + TM_W0_LO, smem_u32(B_hi), smem_u32(B_lo));
             umma_commit(bar_mma);
         }
+        if (t + 1 < t_end) prefetch(t + 1);
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
