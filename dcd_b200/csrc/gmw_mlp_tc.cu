@@ -36,8 +36,10 @@ enum { MODE_FIRST = 0, MODE_B = 1, MODE_CA = 2 };
 
 // ---- operand geometry
 constexpr size_t B_PART_BYTES = (size_t)CH * TE * 2;   // 32 KB: one FP16 part (hi or lo) of a [128 k][128 edge] operand
-constexpr uint32_t B_SBO = 128, B_LBO = 2048;          // MN-major no-swizzle: N-block stride, K-block stride (bytes)
-constexpr uint32_t B_KSTEP = 2 * B_LBO;                // one MMA consumes K = 16 = 2 K-blocks
+// B operand: MN-major, 128-byte swizzle.  Atom = 8 k-rows x 128 B (64 consecutive edges of one channel per row,
+// 16-byte chunks XOR-swizzled by the row); [16 k-atoms][2 n-atoms] atoms of 1 KB.
+constexpr uint32_t B_LBO = 1024, B_SBO = 2048;         // stride between n-atoms, between k-atoms (bytes)
+constexpr uint32_t B_KSTEP = 2 * B_SBO;                // one MMA consumes K = 16 = 2 k-atoms
 constexpr int TC_THREADS = 256;                        // two groups of 4 warps, each with its own tile stream
 constexpr int GROUP_THREADS = 128;
 // tensor memory map (512 columns): resident weights as the A operand, one accumulator per group
@@ -125,9 +127,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
-// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: version 1, layout_type 0)
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): version 1, layout_type 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
 // instruction descriptor: D = F32, A = B = F16, A K-major (TMEM), B MN-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 16) | ((uint32_t)(TE >> 3) << 17) | ((uint32_t)(CH >> 4) << 24);
@@ -148,7 +151,9 @@ __device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, uint32_t a_hi,
     }
 }
 
-// 8 consecutive edges of one input channel -> FP16 hi/lo, one 16-byte store each (MN-major canonical layout)
+// 8 consecutive edges (edge block `eblk`) of one input channel -> FP16 hi/lo, one 16-byte store each into the
+// swizzled MN-major operand.  Conflict-free both for 8 lanes = 8 channels of one edge block (epilogue) and for
+// 8 lanes = {4 edge blocks} x {channels c, c+4} (coalesced source loads).
 __device__ __forceinline__ void store_b8(unsigned char* b_hi, unsigned char* b_lo, int ch, int eblk, const float (&v)[8]) {
     __half2 h[4], l[4];
 #pragma unroll
@@ -157,7 +162,8 @@ __device__ __forceinline__ void store_b8(unsigned char* b_hi, unsigned char* b_l
         h[q] = __halves2half2(h0, h1);
         l[q] = __halves2half2(__float2half_rn(v[2 * q] - __half2float(h0)), __float2half_rn(v[2 * q + 1] - __half2float(h1)));
     }
-    const uint32_t off = (uint32_t)eblk * B_SBO + (uint32_t)(ch >> 3) * B_LBO + (uint32_t)(ch & 7) * 16;
+    const uint32_t krow = (uint32_t)ch & 7u;
+    const uint32_t off = (uint32_t)(ch >> 3) * B_SBO + (uint32_t)(eblk >> 3) * B_LBO + krow * 128u + ((((uint32_t)eblk & 7u) ^ krow) << 4);
     *reinterpret_cast<uint4*>(b_hi + off) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(b_lo + off) = *reinterpret_cast<const uint4*>(l);
 }
@@ -218,7 +224,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const int group = warp >> 2, gwarp = warp & 3, gtid = tid & (GROUP_THREADS - 1);
     const int E = L.E, EP = L.EP, T = L.T;
 
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* B_hi = smem + SM_B + (size_t)group * 2 * B_PART_BYTES;
     unsigned char* B_lo = B_hi + B_PART_BYTES;
     float2* stat_s = reinterpret_cast<float2*>(smem + SM_STAT) + group * CH;
@@ -270,29 +276,29 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 
     uint32_t mma_phase = 0;
     int64_t stat_obj = -1;
-    // Source-tile prefetch: the first PRE of this thread's 16 items (8 channels x 8 edges each) of the NEXT tile
-    // are loaded into registers right after the current tile's operand is handed to the tensor core, so that
-    // their HBM latency is covered by the MMA waits and both epilogues.
+    // Source-tile mapping: a warp owns 32 channels = 16 row pairs (c, c+4); per pair every lane loads float4 #lane of
+    // both rows (two fully coalesced 512-byte requests) and lane pairs swap halves by shuffle, after which an even
+    // lane holds the 8 edges of block lane/2 of row c and the odd lane those of row c+4.
+    // Prefetch: the first PRE row pairs of the NEXT tile are loaded into registers right after the current tile's
+    // operand is handed to the tensor core, so their HBM latency is covered by the MMA waits and both epilogues.
     constexpr int PRE = (MODE == MODE_FIRST) ? 0 : ((MODE == MODE_CA) ? 8 : 16);
     float4 ypre[PRE > 0 ? PRE : 1][2], xpre[(MODE == MODE_CA) ? PRE : 1][2];
-    const int c_sub = lane & 7, j_sub = lane >> 3;
+    auto pair_row = [&](int it) { return gwarp * 32 + (it >> 2) * 8 + (it & 3); };     // row A; row B = A + 4
     auto prefetch = [&](int64_t tt) {
         if (PRE == 0) return;
         const int64_t o = tt / T;
         const int tl = (int)(tt - o * T);
         const int pb = (MODE == MODE_B) ? blk : blk - 1;
-        const float* Y = act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + o * (int64_t)CH * EP;
-        const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + o * (int64_t)CH * EP : nullptr;
+        const float* Y = act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + o * (int64_t)CH * EP + tl * TE + lane * 4;
+        const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + o * (int64_t)CH * EP + tl * TE + lane * 4 : nullptr;
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
-            const int item = gwarp * 16 + u;
-            const int c = (item >> 2) * 8 + c_sub;
-            const int e0 = tl * TE + ((item & 3) * 4 + j_sub) * 8;
-            ypre[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0);
-            ypre[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0 + 4);
+            const int ca = pair_row(u);
+            ypre[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)ca * EP);
+            ypre[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)(ca + 4) * EP);
             if (MODE == MODE_CA) {
-                xpre[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0);
-                xpre[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0 + 4);
+                xpre[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)ca * EP);
+                xpre[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)(ca + 4) * EP);
             }
         }
     };
@@ -336,11 +342,20 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             float* Xn = (MODE == MODE_B) ? nullptr : act_ptr(a.ws, L, net, MODE == MODE_FIRST ? 0 : blk, SLOT_X) + obj_off;
             constexpr int UNR = (MODE == MODE_CA) ? 4 : 8;
             const bool full_tile = valid == TE;
-            // convert 8 edges of channel c and store them as FP16 hi/lo into the operand
-            auto convert = [&](int item, const float4& ya, const float4& yb, const float4& xa, const float4& xb) {
-                const int c = (item >> 2) * 8 + c_sub;      // 64 items: 16 channel groups x 4 quads of edge blocks
-                const int eblk = (item & 3) * 4 + j_sub;
-                const int e0 = tile * TE + eblk * 8;
+            const bool odd = lane & 1;
+            const int eblk = lane >> 1;                      // edge block (8 edges) this lane ends up owning
+            auto swap4 = [&](const float4& mine) {           // exchange a float4 with the neighbouring lane
+                float4 r;
+                r.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+                r.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+                r.z = __shfl_xor_sync(0xffffffffu, mine.z, 1);
+                r.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
+                return r;
+            };
+            // one row pair: ya/yb (xa/xb) = float4 #lane of rows c, c+4
+            auto convert = [&](int it, const float4& ya, const float4& yb, const float4& xa, const float4& xb) {
+                const int ca = pair_row(it);
+                const int c = odd ? ca + 4 : ca;             // the row this lane converts
                 float v[8];
                 if (MODE == MODE_FIRST) {
                     const float b = __ldg(prm + blob_in_b(cin) + c);
@@ -357,11 +372,15 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     }
                 } else {
                     const float2 st = stat_s[c];
-                    const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                    const float4 got = swap4(odd ? ya : yb);  // send the half the neighbour needs
+                    const float4 lo4 = odd ? got : ya, hi4 = odd ? yb : got;
+                    const float yv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
                     if (MODE == MODE_CA) {
-                        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                        const float4 gx = swap4(odd ? xa : xb);
+                        const float4 xl = odd ? gx : xa, xh = odd ? xb : gx;
+                        const float xv[8] = {xl.x, xl.y, xl.z, xl.w, xh.x, xh.y, xh.z, xh.w};
 #pragma unroll
                         for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
                     }
@@ -372,42 +391,44 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                         if (eblk * 8 + q >= valid) v[q] = 0.f;
                 }
                 if (MODE != MODE_B) {
-                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(Xn + (int64_t)c * EP + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    // residual stream: swap halves back so that every lane stores float4 #lane of both rows (coalesced)
+                    const float4 first = make_float4(v[0], v[1], v[2], v[3]), second = make_float4(v[4], v[5], v[6], v[7]);
+                    const float4 got = swap4(odd ? first : second);
+                    float* Xrow = Xn + tile * TE + lane * 4;
+                    *reinterpret_cast<float4*>(Xrow + (int64_t)ca * EP) = odd ? got : first;
+                    *reinterpret_cast<float4*>(Xrow + (int64_t)(ca + 4) * EP) = odd ? second : got;
                 }
                 store_b8(B_hi, B_lo, c, eblk, v);
             };
-            // items loaded here (not covered by the prefetch) first, so their loads overlap the conversion below
+            // row pairs not covered by the prefetch are loaded here; the prefetched ones are converted while they fly
             float4 ybuf[UNR][2], xbuf[UNR][2];
 #pragma unroll 1
             for (int it0 = PRE; it0 < 16; it0 += UNR) {
                 if (MODE != MODE_FIRST) {
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
-                        const int item = gwarp * 16 + it0 + u;
-                        const int c = (item >> 2) * 8 + c_sub;
-                        const int e0 = tile * TE + ((item & 3) * 4 + j_sub) * 8;
-                        ybuf[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0);
-                        ybuf[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)c * EP + e0 + 4);
+                        const int ca = pair_row(it0 + u);
+                        const float* Yl = Y + tile * TE + lane * 4;
+                        ybuf[u][0] = *reinterpret_cast<const float4*>(Yl + (int64_t)ca * EP);
+                        ybuf[u][1] = *reinterpret_cast<const float4*>(Yl + (int64_t)(ca + 4) * EP);
                         if (MODE == MODE_CA) {
-                            xbuf[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0);
-                            xbuf[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)c * EP + e0 + 4);
+                            const float* Xl = Xp + tile * TE + lane * 4;
+                            xbuf[u][0] = *reinterpret_cast<const float4*>(Xl + (int64_t)ca * EP);
+                            xbuf[u][1] = *reinterpret_cast<const float4*>(Xl + (int64_t)(ca + 4) * EP);
                         }
                     }
                 }
-                if (it0 == PRE) {                            // prefetched items are converted while those loads fly
+                if (it0 == PRE) {
 #pragma unroll
                     for (int u = 0; u < PRE; ++u)
-                        convert(gwarp * 16 + u, ypre[u][0], ypre[u][1], xpre[MODE == MODE_CA ? u : 0][0], xpre[MODE == MODE_CA ? u : 0][1]);
+                        convert(u, ypre[u][0], ypre[u][1], xpre[MODE == MODE_CA ? u : 0][0], xpre[MODE == MODE_CA ? u : 0][1]);
                 }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u)
-                    convert(gwarp * 16 + it0 + u, ybuf[u][0], ybuf[u][1], xbuf[u][0], xbuf[u][1]);
+                for (int u = 0; u < UNR; ++u) convert(it0 + u, ybuf[u][0], ybuf[u][1], xbuf[u][0], xbuf[u][1]);
             }
             if (PRE == 16) {                                 // everything came from the prefetch
 #pragma unroll
-                for (int u = 0; u < PRE; ++u)
-                    convert(gwarp * 16 + u, ypre[u][0], ypre[u][1], xpre[0][0], xpre[0][1]);
+                for (int u = 0; u < PRE; ++u) convert(u, ypre[u][0], ypre[u][1], xpre[0][0], xpre[0][1]);
             }
         }
         fence_async_smem();
