@@ -142,6 +142,113 @@ edge_solve_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ k
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, throughput variant: ONE WARP PER OBJECT (used for large N).  No block barrier in the object loop
+// (the per-object barrier of the CTA-per-object kernel is what bounds it at large N): a warp stages its
+// object's keypoint terms in a private shared-memory slice, walks the E edges 32 at a time through a pair
+// table shared by the CTA (coalesced 128-byte stores of the per-edge depths), and reduces the mean with
+// shuffles.  The next object's raw inputs are prefetched into registers (n = 73: 3 keypoints per lane).
+// ---------------------------------------------------------------------------------------------
+template <int NK, int THREADS, bool WRITE_EDGES>
+__global__ void __launch_bounds__(THREADS)
+edge_solve_fwd_warp_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                           const float* __restrict__ rot, const float* __restrict__ K,
+                           int64_t N, int n_rt, float lo, float hi, int flags,
+                           float* __restrict__ depth_edges, float* __restrict__ depth_mean) {
+    constexpr int NWARP = THREADS / 32;
+    const int n = NK > 0 ? NK : n_rt;
+    const int E = n * (n - 1) / 2;
+    constexpr int KPL = NK > 0 ? (NK + 31) / 32 : 1;         // keypoints per lane held in registers (NK > 0)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* kp_all = reinterpret_cast<float4*>(smem_raw);                     // [NWARP][n]
+    uint32_t* tab_s = reinterpret_cast<uint32_t*>(kp_all + NWARP * n);        // [E] byte offsets (i*16) | (j*16) << 16
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < E; e += THREADS) {
+        int i, j;
+        decode_edge(e, n, i, j);
+        tab_s[e] = (uint32_t)(i * 16) | ((uint32_t)(j * 16) << 16);
+    }
+    __syncthreads();
+    float4* kp = kp_all + warp * n;
+    const unsigned char* kpb = reinterpret_cast<const unsigned char*>(kp);
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    const int64_t stride = (int64_t)gridDim.x * NWARP;
+
+    float2 nx_uv[KPL];
+    float nx_p[KPL][3];
+    auto load_raw = [&](int64_t o) {
+        if (NK == 0 || o >= N) return;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int t = lane + q * 32;
+            if (t < n) {
+                nx_uv[q] = __ldg(reinterpret_cast<const float2*>(kps + (o * n + t) * 2));
+                const float* p3 = kps3d + (o * n + t) * 3;
+                nx_p[q][0] = __ldg(p3); nx_p[q][1] = __ldg(p3 + 1); nx_p[q][2] = __ldg(p3 + 2);
+            }
+        }
+    };
+    int64_t obj = (int64_t)blockIdx.x * NWARP + warp;
+    load_raw(obj);
+    for (; obj < N; obj += stride) {
+        float cy = 0.f, fy = 1.f, b3 = 0.f;
+        if (K != nullptr) {
+            const float* Ko = K + obj * 12;
+            if (normalise) { cy = __ldg(Ko + 6); fy = __ldg(Ko + 5); }
+            if (flags & DCD_SUB_B3) b3 = __ldg(Ko + 11);
+        }
+        const float r = __ldg(rot + obj);
+        const float sn = sinf(r), cs = cosf(r);
+        if (NK > 0) {
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const int t = lane + q * 32;
+                if (t < n) kp[t] = keypoint_terms(nx_uv[q].y, nx_p[q][0], nx_p[q][1], nx_p[q][2], sn, cs, normalise, cy, fy);
+            }
+        } else {
+            for (int t = lane; t < n; t += 32) {
+                const float2 uv = __ldg(reinterpret_cast<const float2*>(kps + (obj * n + t) * 2));
+                const float* p3 = kps3d + (obj * n + t) * 3;
+                kp[t] = keypoint_terms(uv.y, __ldg(p3), __ldg(p3 + 1), __ldg(p3 + 2), sn, cs, normalise, cy, fy);
+            }
+        }
+        __syncwarp();
+        load_raw(obj + stride);                              // in flight during the edge loop
+        float acc = 0.f;
+        float* out = WRITE_EDGES ? depth_edges + obj * (int64_t)E : nullptr;
+        int e = lane;
+#pragma unroll 4
+        for (; e + 96 < E; e += 128) {
+            float z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = tab_s[e + 32 * u];
+                const float4 a = *reinterpret_cast<const float4*>(kpb + (p & 0xffffu));
+                const float4 b = *reinterpret_cast<const float4*>(kpb + (p >> 16));
+                z[u] = edge_depth(a, b, lo, hi, b3);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (WRITE_EDGES) __stcs(out + e + 32 * u, z[u]);
+                acc += z[u];
+            }
+        }
+        for (; e < E; e += 32) {
+            const uint32_t p = tab_s[e];
+            const float4 a = *reinterpret_cast<const float4*>(kpb + (p & 0xffffu));
+            const float4 b = *reinterpret_cast<const float4*>(kpb + (p >> 16));
+            const float z = edge_depth(a, b, lo, hi, b3);
+            if (WRITE_EDGES) __stcs(out + e, z);
+            acc += z;
+        }
+        if (depth_mean != nullptr) {
+            acc = warp_sum(acc);
+            if (lane == 0) depth_mean[obj] = __fdiv_rn(acc, (float)E);
+        }
+        __syncwarp();                                        // all lanes done with kp before it is restaged
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // selection: top-k edges by |V| sorted (|V| desc, edge id asc) + their depths / pair masks / mean.
 // One CTA per object; bitonic sort of (key, id) in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -326,7 +433,30 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
                           float* depth_edges, float* depth_mean, cudaStream_t st) {
     constexpr int T = 256;
     const int E = n * (n - 1) / 2;
-    const int64_t max_grid = (int64_t)device_sm_count() * 8;
+    const int sms = device_sm_count();
+    // throughput regime: one warp per object (no per-object block barrier)
+    const size_t wsmem = (size_t)(T / 32) * n * sizeof(float4) + (size_t)E * sizeof(uint32_t);
+    if (N >= (int64_t)sms * 16 && wsmem <= 100 * 1024) {
+        const int64_t want = (N + T / 32 - 1) / (T / 32), cap = (int64_t)sms * 6;
+        const int grid = (int)(want < cap ? want : cap);
+#define DCD_LAUNCH_WARP(NKV, WE)                                                                                   \
+    do {                                                                                                           \
+        if (wsmem > 48 * 1024)                                                                                     \
+            cudaFuncSetAttribute(edge_solve_fwd_warp_kernel<NKV, T, WE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem); \
+        edge_solve_fwd_warp_kernel<NKV, T, WE><<<grid, T, wsmem, st>>>(kps, kps3d, rot, K, N, n, lo, hi, flags,    \
+                                                                       depth_edges, depth_mean);                   \
+    } while (0)
+        if (n == 73) {
+            if (depth_edges) DCD_LAUNCH_WARP(73, true); else DCD_LAUNCH_WARP(73, false);
+        } else {
+            if (depth_edges) DCD_LAUNCH_WARP(0, true); else DCD_LAUNCH_WARP(0, false);
+        }
+#undef DCD_LAUNCH_WARP
+        DCD_CHECK_LAUNCH();
+        return DCD_OK;
+    }
+    // latency regime (a frame's worth of objects): one CTA per object
+    const int64_t max_grid = (int64_t)sms * 8;
     const int grid = (int)(N < max_grid ? N : max_grid);
     size_t smem = (size_t)2 * n * sizeof(float4) + 2 * (T / 32) * sizeof(float);
     if (n == 73) {

@@ -196,3 +196,22 @@ def test_full_size_properties():
     # oracle on a slice
     d_o, _ = O.decode_pairs_kpts_depth(kps[:256], k3[:256], rot[:256], K[:256])
     assert torch.equal(d[:256], d_o)
+
+
+@pytest.mark.parametrize("n", [73, 60])
+def test_throughput_and_latency_kernels_agree(n):
+    """Large batches run the warp-per-object kernel, small ones the CTA-per-object kernel: identical bits."""
+    ob = synth.make_objects(N=4000, n=n, seed=77)
+    kps, k3, rot, K = cu(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+    d_big, _ = dcd_b200.decode_pairs_kpts_depth(kps, k3, rot, K)
+    m_big = dcd_b200.edge_depth_mean(kps, k3, rot, K)
+    for lo in (0, 1777, 3900):
+        sl = slice(lo, lo + 100)
+        d_small, _ = dcd_b200.decode_pairs_kpts_depth(kps[sl], k3[sl], rot[sl], K[sl])
+        assert torch.equal(d_big[sl], d_small)
+        assert rel_err(m_big[sl], dcd_b200.edge_depth_mean(kps[sl], k3[sl], rot[sl], K[sl])) < 1e-6
+    d_o, _ = O.decode_pairs_kpts_depth(kps[:300], k3[:300], rot[:300], K[:300])
+    assert torch.equal(d_big[:300], d_o)
+    Z, _ = dcd_b200.compute_z(cu(ob.kps_norm)[0], k3, rot)
+    Zo, _ = O.compute_z(ob.kps_norm[:200].to(DEV), k3[:200], rot[:200])
+    assert torch.equal(Z[:200], Zo)
