@@ -336,6 +336,21 @@ def main():
                                                              2.0, 80.0, 3, ptr(idx_b), ptr(z_b), 0, 0, st), "select"), reps=5)
     del edges
 
+    # ---- GMW training step, batch 8 per GPU (BASELINE configs[2]): compute_z + forward (saved) + loss + backward
+    tb = 8
+    t_k2, t_k3, t_rot, t_gt = d_k2[:tb].contiguous(), d_k3[:tb].contiguous(), d_rot[:tb].reshape(-1, 1).contiguous(), ob.gt_depth[:tb].to(dev)
+    train_model = dcd_b200.GMW().to(dev).load_reference_state_dict(O.random_state_dict(WEIGHT_SEED))
+
+    def train_step():
+        train_model.zero_grad(set_to_none=True)
+        Zt, idxt = dcd_b200.compute_z(t_k2, t_k3, t_rot)
+        wt, _ = train_model(t_k2, t_k3, t_rot, None)
+        loss, _ = dcd_b200.compute_reg_loss(Zt, wt, t_gt, idxt)
+        loss.backward()
+        if world > 1:
+            ddist.allreduce_gradients(train_model)
+    ms_train = time_kernel(train_step, reps=5)
+
     # ---- reduce over ranks (max time) and report
     times = torch.tensor([ms, e2e_ms, mlp_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -383,6 +398,9 @@ def main():
                                      "hbm_gbs": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9,
                                      "frac_hbm": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                 "edge_select_top1500": {"objects_per_s": sel_n / (ms_sel * 1e-3), "ms": ms_sel, "objects": sel_n},
+                "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": tb * world / (ms_train * 1e-3),
+                                      "what": "configs[2]: compute_z + edge MLP fwd (tcgen05) + softmax aggregate + L1 loss + full backward "
+                                              "(FP32 CUDA cores) for 8 objects per GPU%s; optimizer step excluded" % (" + gradient all-reduce" if world > 1 else "")},
                 "fp32_peak_tflops": fp32_peak,
             },
             "clocks": clocks,

@@ -202,3 +202,29 @@ def test_full_size_properties_gmw():
     with torch.no_grad():
         ref = O.gmw_pipeline(ob.kps_norm[:3], ob.kps_3d[:3], ob.rot_y[:3], sd)
     assert rel_err(a[:3].cpu(), ref) < 1e-5
+
+
+def test_stress_shape_256_keypoints():
+    """BASELINE configs[4] shape: n = 256 keypoints, E = 32 640 edges (255 tiles per object), forward + backward.
+    The reference GMW module hard-codes 73 keypoints, so the oracle restatement is the checker here."""
+    n, depth, N = 256, 2, 2
+    ob = synth.make_objects(N=N, n=n, seed=synth.BASE_SEED + 4)
+    sd = O.random_state_dict(256, depth=depth)
+    model = make_model(sd, depth)
+    k2, k3, rot, gt = cu(ob.kps_norm, ob.kps_3d, ob.rot_y, ob.gt_depth)
+    Z, idx = dcd_b200.compute_z(k2, k3, rot)
+    Zo, idxo = O.compute_z(k2, k3, rot)
+    assert torch.equal(idx, idxo) and torch.equal(Z, Zo) and Z.shape == (N, 32640)
+    w, _ = model(k2, k3, rot, None)
+    loss, zsel = dcd_b200.compute_reg_loss(Z, w, gt, idx)
+    loss.backward()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    w64 = O.gmw_reg_weights(ob.kps_norm.double(), ob.kps_3d.double(), sd64, depth)
+    assert rel_err(w.cpu(), w64) < 2e-4
+    _, z64 = O.compute_reg_loss(Z.cpu().double(), w64, ob.gt_depth.double(), idx.cpu())
+    assert rel_err(zsel.cpu(), z64) < 1e-5
+    fused = dcd_b200.gmw_weighted_depth(k2, k3, rot, model)
+    assert rel_err(fused, zsel) < 1e-6
+    g = model.reference_grads()
+    assert all(torch.isfinite(v).all() for v in g.values())
+    assert float(g["FeatureExtractor4d.conv_0.conv2.0.weight"].abs().max()) > 0
