@@ -40,8 +40,8 @@ constexpr size_t B_PART_BYTES = (size_t)CH * TE * 2;   // 32 KB: one FP16 part (
 // 16-byte chunks XOR-swizzled by the row); [16 k-atoms][2 n-atoms] atoms of 1 KB.
 constexpr uint32_t B_LBO = 1024, B_SBO = 2048;         // stride between n-atoms, between k-atoms (bytes)
 constexpr uint32_t B_KSTEP = 2 * B_SBO;                // one MMA consumes K = 16 = 2 k-atoms
-constexpr int TC_THREADS = 256;                        // two groups of 4 warps, each with its own tile stream
-constexpr int GROUP_THREADS = 128;
+constexpr int TC_THREADS = 512;                        // two groups of 8 warps, each with its own tile stream
+constexpr int GROUP_THREADS = 256;
 // tensor memory map (512 columns): resident weights as the A operand, one accumulator per group
 constexpr uint32_t TM_W0_HI = 0, TM_W0_LO = 64, TM_W1_HI = 128, TM_W1_LO = 192, TM_D0 = 256, TM_D1 = 384;
 constexpr uint32_t TMEM_COLS = 512;
@@ -50,7 +50,8 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr size_t SM_B = 0;                                       // [group]{hi, lo} : 4 x 32 KB
 constexpr size_t SM_STAT = SM_B + 4 * B_PART_BYTES;              // [group][128] float2
 constexpr size_t SM_F = SM_STAT + 2 * CH * sizeof(float2);       // [group][128 edges][8] floats (FIRST)
-constexpr size_t SM_BAR = SM_F + 2 * TE * 8 * sizeof(float);     // mbarriers + tmem pointer
+constexpr size_t SM_HALF = SM_F + 2 * TE * 8 * sizeof(float);    // [group][128] float4: statistics of the upper column half
+constexpr size_t SM_BAR = SM_HALF + 2 * CH * sizeof(float4);     // mbarriers + tmem pointer
 constexpr size_t kTcSmem = SM_BAR + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,9 +194,8 @@ __global__ void __launch_bounds__(256) tc_weight_scales_kernel(const float* __re
 // One output-channel row of a weight matrix -> FP16 hi/lo pairs -> tensor memory (A operand, K-major:
 // lane = out channel, 32-bit column c holds input channels 2c (low half) and 2c+1).
 __device__ __forceinline__ void load_weight_row_to_tmem(const float* __restrict__ Wt, float scale, int row,
-                                                        uint32_t t_hi, uint32_t t_lo) {
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+                                                        uint32_t t_hi, uint32_t t_lo, int half) {
+    {
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -221,7 +221,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const int cin = net == 0 ? 4 : 6;
     const float* __restrict__ prm = a.params[net];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int group = warp >> 2, gwarp = warp & 3, gtid = tid & (GROUP_THREADS - 1);
+    const int group = warp >> 3, gwarp = warp & 7, gtid = tid & (GROUP_THREADS - 1);
+    const int quarter = gwarp & 3, hsel = gwarp >> 2;      // TMEM lane quarter / column half owned in the epilogues
     const int E = L.E, EP = L.EP, T = L.T;
 
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -229,6 +230,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     unsigned char* B_lo = B_hi + B_PART_BYTES;
     float2* stat_s = reinterpret_cast<float2*>(smem + SM_STAT) + group * CH;
     float* f_s = reinterpret_cast<float*>(smem + SM_F) + group * TE * 8;
+    float4* half_s = reinterpret_cast<float4*>(smem + SM_HALF) + group * CH;
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + SM_BAR) + group;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);
 
@@ -245,25 +247,25 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int ch = 32 * gwarp + lane;                       // this thread's TMEM lane = output channel
-    const uint32_t lane_off = (uint32_t)(32 * gwarp) << 16;
+    const int ch = 32 * quarter + lane;                     // this thread's TMEM lane = output channel
+    const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
     const float2 sc0 = __ldg(scales + mat0);
     const float2 sc1 = (MODE != MODE_B) ? __ldg(scales + mat0 + 1) : make_float2(0.f, 0.f);
     if (MODE == MODE_B) {
         if (group == 0)
-            load_weight_row_to_tmem(prm + blob_w(cin, blk, 2), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO);
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 2), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO, hsel);
     } else {
         if (group == 0)
-            load_weight_row_to_tmem(prm + blob_w(cin, blk, 0), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO);
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 0), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO, hsel);
         else
-            load_weight_row_to_tmem(prm + blob_w(cin, blk, 1), sc1.x, ch, tmem_base + lane_off + TM_W1_HI, tmem_base + lane_off + TM_W1_LO);
+            load_weight_row_to_tmem(prm + blob_w(cin, blk, 1), sc1.x, ch, tmem_base + lane_off + TM_W1_HI, tmem_base + lane_off + TM_W1_LO, hsel);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
     const uint32_t tmem_d = tmem_base + (group == 0 ? TM_D0 : TM_D1);
-    const uint32_t t_lane = tmem_d + lane_off;
+    const uint32_t t_lane = tmem_d + lane_off + (uint32_t)(hsel * 64);
     const float un0 = sc0.y, un1 = sc1.y;
     const float bias0 = __ldg(prm + blob_b(cin, blk, w0) + ch);
     const float bias1 = (MODE != MODE_B) ? __ldg(prm + blob_b(cin, blk, 1) + ch) : 0.f;
@@ -281,9 +283,10 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     // lane holds the 8 edges of block lane/2 of row c and the odd lane those of row c+4.
     // Prefetch: the first PRE row pairs of the NEXT tile are loaded into registers right after the current tile's
     // operand is handed to the tensor core, so their HBM latency is covered by the MMA waits and both epilogues.
-    constexpr int PRE = (MODE == MODE_FIRST) ? 0 : ((MODE == MODE_CA) ? 8 : 16);
+    constexpr int NPAIR = 8;                                // row pairs per warp (16 channels)
+    constexpr int PRE = (MODE == MODE_FIRST) ? 0 : ((MODE == MODE_CA) ? 2 : 8);
     float4 ypre[PRE > 0 ? PRE : 1][2], xpre[(MODE == MODE_CA) ? PRE : 1][2];
-    auto pair_row = [&](int it) { return gwarp * 32 + (it >> 2) * 8 + (it & 3); };     // row A; row B = A + 4
+    auto pair_row = [&](int it) { return gwarp * 16 + (it >> 2) * 8 + (it & 3); };     // row A; row B = A + 4
     auto prefetch = [&](int64_t tt) {
         if (PRE == 0) return;
         const int64_t o = tt / T;
@@ -311,7 +314,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 
         // ---- source tile -> B operand (hi/lo)
         if (MODE == MODE_FIRST) {
-            {
+            if (gtid < TE) {
                 const int e = tile * TE + gtid;
                 int i, j;
                 decode_edge(e < E ? e : E - 1, L.n, i, j);
@@ -331,7 +334,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
         } else if (stat_obj != obj) {
             const int pb = (MODE == MODE_B) ? blk : blk - 1;
             const int which = (MODE == MODE_B) ? 0 : 1;
-            stat_s[gtid] = merge_cn_stats(stat_ptr(a.ws, L, net, pb, which) + obj * (int64_t)T * CH, gtid, T, E);
+            if (gtid < CH)
+                stat_s[gtid] = merge_cn_stats(stat_ptr(a.ws, L, net, pb, which) + obj * (int64_t)T * CH, gtid, T, E);
             group_sync(group);
             stat_obj = obj;
         }
@@ -340,7 +344,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             const float* Y = (MODE == MODE_FIRST) ? nullptr : act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + obj_off;
             const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + obj_off : nullptr;
             float* Xn = (MODE == MODE_B) ? nullptr : act_ptr(a.ws, L, net, MODE == MODE_FIRST ? 0 : blk, SLOT_X) + obj_off;
-            constexpr int UNR = (MODE == MODE_CA) ? 4 : 8;
+            constexpr int UNR = (MODE == MODE_CA) ? 2 : 8;
             const bool full_tile = valid == TE;
             const bool odd = lane & 1;
             const int eblk = lane >> 1;                      // edge block (8 edges) this lane ends up owning
@@ -403,7 +407,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             // row pairs not covered by the prefetch are loaded here; the prefetched ones are converted while they fly
             float4 ybuf[UNR][2], xbuf[UNR][2];
 #pragma unroll 1
-            for (int it0 = PRE; it0 < 16; it0 += UNR) {
+            for (int it0 = PRE; it0 < NPAIR; it0 += UNR) {
                 if (MODE != MODE_FIRST) {
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
@@ -426,7 +430,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) convert(it0 + u, ybuf[u][0], ybuf[u][1], xbuf[u][0], xbuf[u][1]);
             }
-            if (PRE == 16) {                                 // everything came from the prefetch
+            if (PRE == NPAIR) {                              // everything came from the prefetch
 #pragma unroll
                 for (int u = 0; u < PRE; ++u) convert(u, ypre[u][0], ypre[u][1], xpre[0][0], xpre[0][1]);
             }
@@ -447,9 +451,9 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 
         if (MODE != MODE_B) {
             // preconv output: + bias, kept on chip as the operand of conv1
-            float* Pg = L.save ? act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off + (int64_t)ch * EP + tile * TE : nullptr;
+            float* Pg = L.save ? act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off + (int64_t)ch * EP + tile * TE + hsel * 64 : nullptr;
 #pragma unroll 1
-            for (int part = 0; part < 4; ++part) {
+            for (int part = 0; part < 2; ++part) {
                 float v[32];
                 tmem_ld32(t_lane + part * 32, v);
 #pragma unroll
@@ -463,7 +467,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                 for (int bq = 0; bq < 4; ++bq) {
                     const float w8[8] = {v[bq * 8], v[bq * 8 + 1], v[bq * 8 + 2], v[bq * 8 + 3],
                                          v[bq * 8 + 4], v[bq * 8 + 5], v[bq * 8 + 6], v[bq * 8 + 7]};
-                    store_b8(B_hi, B_lo, ch, part * 4 + bq, w8);
+                    store_b8(B_hi, B_lo, ch, hsel * 8 + part * 4 + bq, w8);
                 }
             }
             fence_async_smem();
@@ -489,10 +493,10 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             float4* stage = reinterpret_cast<float4*>(B_hi);            // [128 rows][32 slots] = 64 KB (B_hi + B_lo)
             float mean = 0.f, M2 = 0.f, cnt = 0.f;
 #pragma unroll 1
-            for (int part = 0; part < 4; ++part) {
+            for (int part = 0; part < 2; ++part) {
                 float v[32];
                 tmem_ld32(t_lane + part * 32, v);
-                const int nv = max(0, min(32, valid - part * 32));
+                const int nv = max(0, min(32, valid - hsel * 64 - part * 32));
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -501,7 +505,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    stage[ch * 32 + ((part * 8 + q) ^ (ch & 31))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    stage[ch * 32 + ((hsel * 16 + part * 8 + q) ^ (ch & 31))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 if (nv > 0) {
                     const float pm = s / (float)nv;
                     float pm2 = 0.f;
@@ -518,13 +522,22 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     cnt = tot;
                 }
             }
-            stat_ptr(a.ws, L, net, blk, MODE == MODE_B ? 1 : 0)[(obj * T + tile) * (int64_t)CH + ch] = make_float2(mean, M2);
+            if (hsel == 1) half_s[ch] = make_float4(mean, M2, cnt, 0.f);
             tc_fence_before();
             group_sync(group);                                // staging complete; TMEM reads done
+            if (hsel == 0) {
+                const float4 o = half_s[ch];                  // Chan merge with the upper 64-edge half
+                if (o.z > 0.f) {
+                    const float tot = cnt + o.z, delta = o.x - mean;
+                    mean += delta * (o.z / tot);
+                    M2 += o.y + delta * delta * (cnt * o.z / tot);
+                }
+                stat_ptr(a.ws, L, net, blk, MODE == MODE_B ? 1 : 0)[(obj * T + tile) * (int64_t)CH + ch] = make_float2(mean, M2);
+            }
             float* Yo = act_ptr(a.ws, L, net, blk, MODE == MODE_B ? SLOT_Y2 : SLOT_Y1) + obj_off + tile * TE;
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const int r = gwarp * 32 + i;
+            for (int i = 0; i < 16; ++i) {
+                const int r = gwarp * 16 + i;
                 const float4 val = stage[r * 32 + (lane ^ (r & 31))];
                 *reinterpret_cast<float4*>(Yo + (int64_t)r * EP + lane * 4) = val;
             }
