@@ -318,7 +318,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                 const int e = tile * TE + gtid;
                 int i, j;
                 decode_edge(e < E ? e : E - 1, L.n, i, j);
-                float* f = f_s + gtid * 8;
+                float f[6];
                 if (net == 0) {
                     const float2 pi = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + i) * 2));
                     const float2 pj = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + j) * 2));
@@ -329,6 +329,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     f[0] = __ldg(pi); f[1] = __ldg(pi + 1); f[2] = __ldg(pi + 2);
                     f[3] = __ldg(pj); f[4] = __ldg(pj + 1); f[5] = __ldg(pj + 2);
                 }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) f_s[r * TE + gtid] = f[r];     // feature-major: conflict-free both ways
             }
             group_sync(group);
         } else if (stat_obj != obj) {
@@ -357,6 +359,16 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                 return r;
             };
             // one row pair: ya/yb (xa/xb) = float4 #lane of rows c, c+4
+            float fe[6][8];                                  // FIRST: the 6 edge features of this lane's 8 edges
+            if (MODE == MODE_FIRST) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const float4 f0 = *reinterpret_cast<const float4*>(f_s + r * TE + eblk * 8);
+                    const float4 f1 = *reinterpret_cast<const float4*>(f_s + r * TE + eblk * 8 + 4);
+                    fe[r][0] = f0.x; fe[r][1] = f0.y; fe[r][2] = f0.z; fe[r][3] = f0.w;
+                    fe[r][4] = f1.x; fe[r][5] = f1.y; fe[r][6] = f1.z; fe[r][7] = f1.w;
+                }
+            }
             auto convert = [&](int it, const float4& ya, const float4& yb, const float4& xa, const float4& xb) {
                 const int ca = pair_row(it);
                 const int c = odd ? ca + 4 : ca;             // the row this lane converts
@@ -368,10 +380,9 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + c) : 0.f;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float* f = f_s + (eblk * 8 + q) * 8;
                         float x = b;
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) x = fmaf(wq[r], f[r], x);
+                        for (int r = 0; r < 6; ++r) x = fmaf(wq[r], fe[r][q], x);
                         v[q] = x;
                     }
                 } else {
