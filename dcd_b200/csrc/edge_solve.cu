@@ -2,22 +2,21 @@
 //
 // Replaces DGDE/model/anno_encoder.py:313-390 (decode_pairs_kpts_depth + get_up) and the solve/top-k of
 // GMW/main.py:351-416 (compute_z).  Design:
-//   * one CTA works on one object at a time (persistent grid-stride loop over objects);
 //   * the object's keypoints (2D v, 3D X/Y/Z, yaw, intrinsics: ~1.5 KB) are read from HBM once, reduced
-//     to 16 B of per-keypoint terms {v, Y, v*C, C} and staged in shared memory (double buffered, one
-//     __syncthreads per object);
-//   * every thread owns a FIXED set of edges, so for the production shape (n = 73) the (i,j) pairs live
-//     in registers for the whole kernel; edges are never materialised as an n x n matrix;
-//   * per-object sums use warp shuffles + a fixed-order cross-warp sum (deterministic).
+//     to 16 B of per-keypoint terms {v, Y, v*C, C} and staged in shared memory; edges are enumerated by
+//     index (never materialised as an n x n matrix) and every per-edge operation is rounded like the
+//     reference's FP32 torch ops;
+//   * throughput regime (N >= 16 x SMs): ONE WARP PER OBJECT, no block barrier in the object loop, the
+//     (i,j) byte offsets come from a pair table shared by the CTA, next object's inputs prefetched in
+//     registers, per-object mean by warp shuffles;
+//   * latency regime (a frame's worth of objects): ONE CTA PER OBJECT, every thread owns a fixed set of
+//     edges whose (i,j) offsets live in registers (n = 73), double-buffered staging with one
+//     __syncthreads per object, fixed-order cross-warp sum (deterministic).
 #include "dcd_common.cuh"
 
 namespace dcd {
 
 namespace {
-
-struct ObjScalars {
-    float s, c, cy, fy, b3;
-};
 
 // Stage one object's per-keypoint terms into shared memory.
 template <int THREADS>

@@ -508,24 +508,36 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                 float v[32];
                 tmem_ld32(t_lane + part * 32, v);
                 const int nv = max(0, min(32, valid - hsel * 64 - part * 32));
-                float s = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = fmaf(v[i], un, bias);
-                    if (i < nv) s += v[i];
-                }
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], un, bias);
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     stage[ch * 32 + ((hsel * 16 + part * 8 + q) ^ (ch & 31))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 if (nv > 0) {
-                    const float pm = s / (float)nv;
-                    float pm2 = 0.f;
+                    float pm, pm2 = 0.f;
+                    if (nv == 32) {                          // full part (all but the object's last tile): no predication
+                        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nv) {
+                        for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+                        pm = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 32.0f);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
                             const float d = v[i] - pm;
                             pm2 = fmaf(d, d, pm2);
                         }
+                    } else {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nv) sum += v[i];
+                        pm = sum / (float)nv;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nv) {
+                                const float d = v[i] - pm;
+                                pm2 = fmaf(d, d, pm2);
+                            }
+                    }
                     const float nb = (float)nv, tot = cnt + nb;       // Chan merge of the 32-edge parts
                     const float delta = pm - mean;
                     mean += delta * (nb / tot);

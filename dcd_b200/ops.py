@@ -14,6 +14,7 @@ plus fused fast paths for callers that do not need the per-edge intermediates:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -23,6 +24,7 @@ from . import _lib
 from ._lib import check, f32c, ptr, require_cuda, stream_ptr
 from .weights import NET_DEPTH, NET_NAMES, blob_size, pack_state_dict, unpack_blob
 
+_CHECK_FINITE = os.environ.get("DCD_B200_CHECK_FINITE", "0") == "1"   # debug: synchronising range check of GMW.forward
 K_SEL = 1500                 # anno_encoder.py:378, GMW/main.py:413
 DGDE_CLAMP = (2.0, 80.0)     # anno_encoder.py:375
 GMW_CLAMP = (0.1, 80.0)      # GMW/main.py:410
@@ -321,6 +323,9 @@ class GMW(nn.Module):
             raise ValueError("kpts_2d must be [b,n,2] and kpts_3d [b,n,3]")
         need_grad = torch.is_grad_enabled() and (self.params4.requires_grad or self.params6.requires_grad)
         reg_w = _GmwWeights.apply(k2, k3, self.params4, self.params6, self.depth, need_grad)
+        if _CHECK_FINITE and not bool(torch.isfinite(reg_w).all()):
+            # the tensor-core path carries activations as FP16 hi+lo pairs: |activation| must stay below 65504
+            raise FloatingPointError("dcd_b200.GMW: non-finite edge weights (activation outside the FP16 hi/lo range?)")
         return reg_w, None
 
 
