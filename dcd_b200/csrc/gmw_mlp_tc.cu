@@ -128,6 +128,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one lane moves the 8 FP32 edges of one operand chunk
+struct F8 {
+    float v[8];
+};
+__device__ __forceinline__ F8 ld256(const float* p) {
+    F8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): version 1, layout_type 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
@@ -278,31 +295,28 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
 
     uint32_t mma_phase = 0;
     int64_t stat_obj = -1;
-    // Source-tile mapping: a warp owns 32 channels = 16 row pairs (c, c+4); per pair every lane loads float4 #lane of
-    // both rows (two fully coalesced 512-byte requests) and lane pairs swap halves by shuffle, after which an even
-    // lane holds the 8 edges of block lane/2 of row c and the odd lane those of row c+4.
+    // Source-tile mapping: a warp owns 16 channels = 8 row pairs (c, c+1); per pair lanes 0-15 take row c and lanes
+    // 16-31 row c+1, each lane one 256-bit load of the 8 edges of block (lane & 15): two fully used 512-byte rows
+    // per request, and the lane already holds exactly one 16-byte chunk of the FP16 operand (no shuffles).
     // Prefetch: the first PRE row pairs of the NEXT tile are loaded into registers right after the current tile's
     // operand is handed to the tensor core, so their HBM latency is covered by the MMA waits and both epilogues.
     constexpr int NPAIR = 8;                                // row pairs per warp (16 channels)
     constexpr int PRE = (MODE == MODE_FIRST) ? 0 : ((MODE == MODE_CA) ? 2 : 8);
-    float4 ypre[PRE > 0 ? PRE : 1][2], xpre[(MODE == MODE_CA) ? PRE : 1][2];
-    auto pair_row = [&](int it) { return gwarp * 16 + (it >> 2) * 8 + (it & 3); };     // row A; row B = A + 4
+    F8 ypre[PRE > 0 ? PRE : 1], xpre[(MODE == MODE_CA) ? PRE : 1];
+    const int eblk = lane & 15;                             // edge block (8 edges) this lane converts
+    auto lane_row = [&](int it) { return gwarp * 16 + it * 2 + (lane >> 4); };
     auto prefetch = [&](int64_t tt) {
         if (PRE == 0) return;
         const int64_t o = tt / T;
         const int tl = (int)(tt - o * T);
         const int pb = (MODE == MODE_B) ? blk : blk - 1;
-        const float* Y = act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + o * (int64_t)CH * EP + tl * TE + lane * 4;
-        const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + o * (int64_t)CH * EP + tl * TE + lane * 4 : nullptr;
+        const float* Y = act_ptr(a.ws, L, net, pb, MODE == MODE_B ? SLOT_Y1 : SLOT_Y2) + o * (int64_t)CH * EP + tl * TE + eblk * 8;
+        const float* Xp = (MODE == MODE_CA) ? act_ptr(a.ws, L, net, blk - 1, SLOT_X) + o * (int64_t)CH * EP + tl * TE + eblk * 8 : nullptr;
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
-            const int ca = pair_row(u);
-            ypre[u][0] = *reinterpret_cast<const float4*>(Y + (int64_t)ca * EP);
-            ypre[u][1] = *reinterpret_cast<const float4*>(Y + (int64_t)(ca + 4) * EP);
-            if (MODE == MODE_CA) {
-                xpre[u][0] = *reinterpret_cast<const float4*>(Xp + (int64_t)ca * EP);
-                xpre[u][1] = *reinterpret_cast<const float4*>(Xp + (int64_t)(ca + 4) * EP);
-            }
+            const int c = lane_row(u);
+            ypre[u] = ld256(Y + (int64_t)c * EP);
+            if (MODE == MODE_CA) xpre[u] = ld256(Xp + (int64_t)c * EP);
         }
     };
     if (t_begin < t_end) prefetch(t_begin);
@@ -348,17 +362,6 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             float* Xn = (MODE == MODE_B) ? nullptr : act_ptr(a.ws, L, net, MODE == MODE_FIRST ? 0 : blk, SLOT_X) + obj_off;
             constexpr int UNR = (MODE == MODE_CA) ? 2 : 8;
             const bool full_tile = valid == TE;
-            const bool odd = lane & 1;
-            const int eblk = lane >> 1;                      // edge block (8 edges) this lane ends up owning
-            auto swap4 = [&](const float4& mine) {           // exchange a float4 with the neighbouring lane
-                float4 r;
-                r.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-                r.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-                r.z = __shfl_xor_sync(0xffffffffu, mine.z, 1);
-                r.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
-                return r;
-            };
-            // one row pair: ya/yb (xa/xb) = float4 #lane of rows c, c+4
             float fe[6][8];                                  // FIRST: the 6 edge features of this lane's 8 edges
             if (MODE == MODE_FIRST) {
 #pragma unroll
@@ -369,9 +372,9 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     fe[r][4] = f1.x; fe[r][5] = f1.y; fe[r][6] = f1.z; fe[r][7] = f1.w;
                 }
             }
-            auto convert = [&](int it, const float4& ya, const float4& yb, const float4& xa, const float4& xb) {
-                const int ca = pair_row(it);
-                const int c = odd ? ca + 4 : ca;             // the row this lane converts
+            // one operand chunk: 8 edges of channel c
+            auto convert = [&](int it, const F8& yy, const F8& xx) {
+                const int c = lane_row(it);
                 float v[8];
                 if (MODE == MODE_FIRST) {
                     const float b = __ldg(prm + blob_in_b(cin) + c);
@@ -387,17 +390,11 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     }
                 } else {
                     const float2 st = stat_s[c];
-                    const float4 got = swap4(odd ? ya : yb);  // send the half the neighbour needs
-                    const float4 lo4 = odd ? got : ya, hi4 = odd ? yb : got;
-                    const float yv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.x) * st.y;
+                    for (int q = 0; q < 8; ++q) v[q] = (yy.v[q] - st.x) * st.y;
                     if (MODE == MODE_CA) {
-                        const float4 gx = swap4(odd ? xa : xb);
-                        const float4 xl = odd ? gx : xa, xh = odd ? xb : gx;
-                        const float xv[8] = {xl.x, xl.y, xl.z, xl.w, xh.x, xh.y, xh.z, xh.w};
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xv[q];
+                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f) + xx.v[q];
                     }
                 }
                 if (!full_tile) {
@@ -405,45 +402,31 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
                     for (int q = 0; q < 8; ++q)
                         if (eblk * 8 + q >= valid) v[q] = 0.f;
                 }
-                if (MODE != MODE_B) {
-                    // residual stream: swap halves back so that every lane stores float4 #lane of both rows (coalesced)
-                    const float4 first = make_float4(v[0], v[1], v[2], v[3]), second = make_float4(v[4], v[5], v[6], v[7]);
-                    const float4 got = swap4(odd ? first : second);
-                    float* Xrow = Xn + tile * TE + lane * 4;
-                    *reinterpret_cast<float4*>(Xrow + (int64_t)ca * EP) = odd ? got : first;
-                    *reinterpret_cast<float4*>(Xrow + (int64_t)(ca + 4) * EP) = odd ? second : got;
-                }
+                if (MODE != MODE_B) st256(Xn + (int64_t)c * EP + tile * TE + eblk * 8, v);   // residual stream
                 store_b8(B_hi, B_lo, c, eblk, v);
             };
             // row pairs not covered by the prefetch are loaded here; the prefetched ones are converted while they fly
-            float4 ybuf[UNR][2], xbuf[UNR][2];
+            F8 ybuf[UNR], xbuf[(MODE == MODE_CA) ? UNR : 1];
 #pragma unroll 1
             for (int it0 = PRE; it0 < NPAIR; it0 += UNR) {
                 if (MODE != MODE_FIRST) {
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
-                        const int ca = pair_row(it0 + u);
-                        const float* Yl = Y + tile * TE + lane * 4;
-                        ybuf[u][0] = *reinterpret_cast<const float4*>(Yl + (int64_t)ca * EP);
-                        ybuf[u][1] = *reinterpret_cast<const float4*>(Yl + (int64_t)(ca + 4) * EP);
-                        if (MODE == MODE_CA) {
-                            const float* Xl = Xp + tile * TE + lane * 4;
-                            xbuf[u][0] = *reinterpret_cast<const float4*>(Xl + (int64_t)ca * EP);
-                            xbuf[u][1] = *reinterpret_cast<const float4*>(Xl + (int64_t)(ca + 4) * EP);
-                        }
+                        const int c = lane_row(it0 + u);
+                        ybuf[u] = ld256(Y + (int64_t)c * EP + tile * TE + eblk * 8);
+                        if (MODE == MODE_CA) xbuf[u] = ld256(Xp + (int64_t)c * EP + tile * TE + eblk * 8);
                     }
                 }
                 if (it0 == PRE) {
 #pragma unroll
-                    for (int u = 0; u < PRE; ++u)
-                        convert(u, ypre[u][0], ypre[u][1], xpre[MODE == MODE_CA ? u : 0][0], xpre[MODE == MODE_CA ? u : 0][1]);
+                    for (int u = 0; u < PRE; ++u) convert(u, ypre[u], xpre[MODE == MODE_CA ? u : 0]);
                 }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) convert(it0 + u, ybuf[u][0], ybuf[u][1], xbuf[u][0], xbuf[u][1]);
+                for (int u = 0; u < UNR; ++u) convert(it0 + u, ybuf[u], xbuf[MODE == MODE_CA ? u : 0]);
             }
             if (PRE == NPAIR) {                              // everything came from the prefetch
 #pragma unroll
-                for (int u = 0; u < PRE; ++u) convert(u, ypre[u][0], ypre[u][1], xpre[0][0], xpre[0][1]);
+                for (int u = 0; u < PRE; ++u) convert(u, ypre[u], xpre[0]);
             }
         }
         fence_async_smem();
