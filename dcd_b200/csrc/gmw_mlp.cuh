@@ -6,9 +6,6 @@ namespace dcd {
 
 constexpr int CH = DCD_NET_CH;   // 128 channels
 constexpr int TE = 128;          // edges per tile
-constexpr int LD = 132;          // padded shared-memory row stride (floats)
-constexpr int KC = 16;           // k-chunk of the streamed weight matrix
-constexpr int MLP_THREADS = 256;
 
 // ---- parameter blob (per net) : W_in^T [Cin][128], b_in[128], then per block {Wp^T,bp,W1^T,b1,W2^T,b2}
 __host__ __device__ inline int64_t blob_in_w() { return 0; }
