@@ -400,6 +400,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                     const float4 g = *reinterpret_cast<const float4*>(dst);
                     val.x += g.x; val.y += g.y; val.z += g.z; val.w += g.w;
                 }
+                // padded columns (edge >= E) hold no data: keep them zero and out of the running maximum
+                const int c0 = lane * 4;
+                if (c0 + 0 >= valid) val.x = 0.f;
+                if (c0 + 1 >= valid) val.y = 0.f;
+                if (c0 + 2 >= valid) val.z = 0.f;
+                if (c0 + 3 >= valid) val.w = 0.f;
                 *reinterpret_cast<float4*>(dst) = val;
                 omax = fmaxf(omax, fmaxf(fmaxf(fabsf(val.x), fabsf(val.y)), fmaxf(fabsf(val.z), fabsf(val.w))));
             }

@@ -214,8 +214,14 @@ def compute_z(kpts_2d, kpts_3d, pred_rot, num_k: int = K_SEL) -> Tuple[torch.Ten
 # ---------------------------------------------------------------------------------------------
 # GMW edge weights + aggregation
 # ---------------------------------------------------------------------------------------------
+POISON_WORKSPACES = os.environ.get("DCD_B200_POISON", "0") == "1"   # debug/tests: NaN-fill every workspace first
+
+
 def _alloc_bytes(nbytes: int, dev) -> torch.Tensor:
-    return torch.empty(((nbytes + 255) // 256 * 64,), dtype=torch.float32, device=dev)
+    t = torch.empty(((nbytes + 255) // 256 * 64,), dtype=torch.float32, device=dev)
+    if POISON_WORKSPACES:
+        t.fill_(float("nan"))       # the kernels must never read what they did not write
+    return t
 
 
 class _GmwWeights(torch.autograd.Function):

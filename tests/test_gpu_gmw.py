@@ -228,3 +228,25 @@ def test_stress_shape_256_keypoints():
     g = model.reference_grads()
     assert all(torch.isfinite(v).all() for v in g.values())
     assert float(g["FeatureExtractor4d.conv_0.conv2.0.weight"].abs().max()) > 0
+
+
+def test_kernels_never_read_uninitialised_workspace(golden, monkeypatch):
+    """All workspaces NaN-filled before use: forward, fused inference and backward must be unaffected
+    (padded edge columns, unused statistics slots and partial buffers may not leak into results)."""
+    from dcd_b200 import ops
+    G = golden("gmw_n73_N4")
+    sd = O.random_state_dict(int(G["weight_seed"]))
+    k2, k3, rot, gt = cu(G["kps_norm"], G["kps_3d"], G["rot_y"], G["gt_depth"])
+    results = []
+    for poison in (False, True):
+        monkeypatch.setattr(ops, "POISON_WORKSPACES", poison)
+        model = make_model(sd)
+        Z, idx = dcd_b200.compute_z(k2, k3, rot)
+        w, _ = model(k2, k3, rot, None)
+        loss, zsel = dcd_b200.compute_reg_loss(Z, w, gt, idx)
+        loss.backward()
+        fused = dcd_b200.gmw_weighted_depth(k2, k3, rot, model)
+        results.append((w.detach().clone(), zsel.detach().clone(), fused.clone(), model.params4.grad.clone(), model.params6.grad.clone()))
+    for a, b in zip(*results):
+        assert torch.isfinite(b).all()
+        assert torch.equal(a, b)
