@@ -380,7 +380,10 @@ def main():
             "roofline": {"kernel": "mlp_tc_kernel<FIRST|B|CA> (edge-feature MLP: 36 GEMM layers x 2 nets on tcgen05, FP16x3 split, "
                                    "FP32 accumulate in TMEM)", "bound": "tensor",
                          "achieved": mlp_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": mlp_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": mlp_tflops / peaks["bf16_tflops_sustained"],
+                         # ncu dram__bytes_read+write of ONE mlp_tc_kernel<CA> launch on a 2048-object chunk
+                         # (profiles/r01_mlp_tc_kernel.md); the layer-wise schedule's model for that launch is 2048 x 11.0 MB
+                         "traffic": 22.93e9 if chunk == 2048 else None,
                          "peak_source": "%s dense bf16 (sustained, of measured); `achieved` counts the algorithmic FP32 GEMM FLOPs, the "
                                         "tensor pipe executes 3 FP16 MMAs per FP32 product (x3 = %.1f TFLOP/s issued); vs the FP32 "
                                         "CUDA-core roofline (%.1f TFLOP/s) the same number is %.2fx" % (
@@ -399,8 +402,8 @@ def main():
                                      "frac_hbm": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                 "edge_select_top1500": {"objects_per_s": sel_n / (ms_sel * 1e-3), "ms": ms_sel, "objects": sel_n},
                 "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": tb * world / (ms_train * 1e-3),
-                                      "what": "configs[2]: compute_z + edge MLP fwd (tcgen05) + softmax aggregate + L1 loss + full backward "
-                                              "(FP32 CUDA cores) for 8 objects per GPU%s; optimizer step excluded" % (" + gradient all-reduce" if world > 1 else "")},
+                                      "what": "configs[2]: compute_z + edge MLP fwd + softmax aggregate + L1 loss + full backward (all GEMMs on "
+                                              "tcgen05) for 8 objects per GPU%s; optimizer step excluded" % (" + gradient all-reduce" if world > 1 else "")},
                 "fp32_peak_tflops": fp32_peak,
             },
             "clocks": clocks,
