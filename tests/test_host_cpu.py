@@ -164,3 +164,36 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "objects/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_patch_against_the_real_reference_objects():
+    """Only where the reference tree is mounted (the build container): install() on the real Anno_Encoder class,
+    GMW/main.py module and GMW nn.Module, weights copied bit-exactly, uninstall() restores everything."""
+    from oracle import ref_loader as rl
+    if not rl.reference_available():
+        pytest.skip("reference tree not mounted")
+    enc = rl.load_dgde_anno_encoder()
+    ref_main, _ = rl.load_gmw()
+    model = rl.new_gmw_model(3)
+    orig_decode = type(enc).decode_pairs_kpts_depth
+    orig_cz, orig_forward = ref_main.compute_z, model.forward
+    n_keys = len(model.state_dict())
+    patch.install(anno_encoder_cls=type(enc), gmw_main=ref_main, gmw_model=model)
+    try:
+        assert ref_main.compute_z is dcd_b200.compute_z
+        assert len(model.state_dict()) == n_keys                     # the fast module is not registered as a sub-module
+        fast = model._dcd_b200
+        back = fast.reference_state_dict()
+        for k, v in model.state_dict().items():
+            assert torch.equal(back[k], v), k
+        ob = synth.make_objects(N=2, n=73, seed=2)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            model(ob.kps_norm, ob.kps_3d, ob.rot_y, None)
+    finally:
+        patch.uninstall()
+    assert type(enc).decode_pairs_kpts_depth is orig_decode and ref_main.compute_z is orig_cz
+    assert model.forward == orig_forward and not hasattr(model, "_dcd_b200")
+    d, _ = enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)        # the reference path works again
+    assert d.shape == (2, 2628)
