@@ -215,8 +215,7 @@ def main():
     N = ob.N
     assert N == hi_obj - lo_obj
     N_total = int(cum[-1])
-    from oracle import dcd_oracle as O      # only for the seeded reference-format weights and the cpu_baseline leg
-    model = dcd_b200.GMW().to(dev).load_reference_state_dict(O.random_state_dict(WEIGHT_SEED))
+    model = dcd_b200.GMW().to(dev).load_reference_state_dict(synth.random_state_dict(WEIGHT_SEED))
     p4, p6 = model.params4.detach(), model.params6.detach()
 
     # host (pinned) and device copies of the inputs
@@ -339,7 +338,7 @@ def main():
     # ---- GMW training step, batch 8 per GPU (BASELINE configs[2]): compute_z + forward (saved) + loss + backward
     tb = 8
     t_k2, t_k3, t_rot, t_gt = d_k2[:tb].contiguous(), d_k3[:tb].contiguous(), d_rot[:tb].reshape(-1, 1).contiguous(), ob.gt_depth[:tb].to(dev)
-    train_model = dcd_b200.GMW().to(dev).load_reference_state_dict(O.random_state_dict(WEIGHT_SEED))
+    train_model = dcd_b200.GMW().to(dev).load_reference_state_dict(synth.random_state_dict(WEIGHT_SEED))
 
     def train_step():
         train_model.zero_grad(set_to_none=True)

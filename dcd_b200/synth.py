@@ -140,3 +140,22 @@ def kitti_val_batch(ragged: bool = True, frames: int = 3769, max_objects: int = 
                     seed: int = BASE_SEED + 1) -> Objects:
     """BASELINE.json configs[1]: 3769 frames, <=50 objects per frame, 73 keypoints."""
     return make_objects(n=n, seed=seed, counts=frame_counts(frames, max_objects, ragged, seed))
+
+
+def random_state_dict(seed: int, depth: int = 12, channels: int = 128):
+    """Seeded random GMW weights with torch's Conv1d default init bounds, keyed like the reference
+    state_dict (FeatureExtractor{4,6}d.conv_in / conv_<k>.{preconv,conv1,conv2}); for benchmarks."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, cin):
+        bound = 1.0 / math.sqrt(cin)
+        sd[key + ".0.weight"] = (torch.rand((channels, cin, 1), generator=g) * 2 - 1) * bound
+        sd[key + ".0.bias"] = (torch.rand((channels,), generator=g) * 2 - 1) * bound
+
+    for name, cin in (("FeatureExtractor4d", 4), ("FeatureExtractor6d", 6)):
+        conv(name + ".conv_in", cin)
+        for k in range(depth):
+            for sub in ("preconv", "conv1", "conv2"):
+                conv("%s.conv_%d.%s" % (name, k, sub), channels)
+    return sd
