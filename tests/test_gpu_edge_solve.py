@@ -215,3 +215,20 @@ def test_throughput_and_latency_kernels_agree(n):
     Z, _ = dcd_b200.compute_z(cu(ob.kps_norm)[0], k3, rot)
     Zo, _ = O.compute_z(ob.kps_norm[:200].to(DEV), k3[:200], rot[:200])
     assert torch.equal(Z[:200], Zo)
+
+
+def test_full_kitti_val_batch_solve():
+    """The whole BASELINE configs[1] batch (3769 frames, 96 406 objects): fused mean == mean of per-edge depths,
+    clamp bounds, and a 512-object slice bit-identical to the oracle."""
+    ob = synth.kitti_val_batch(ragged=True)
+    assert ob.counts.numel() == 3769 and int(ob.counts.max()) <= 50
+    kps, k3, rot, K = cu(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+    mean = dcd_b200.edge_depth_mean(kps, k3, rot, K)
+    d, _ = dcd_b200.decode_pairs_kpts_depth(kps[:20000], k3[:20000], rot[:20000], K[:20000])
+    assert rel_err(mean[:20000], d.mean(1)) < 1e-6
+    lo = 50000
+    d_o, _ = O.decode_pairs_kpts_depth(kps[lo:lo + 512], k3[lo:lo + 512], rot[lo:lo + 512], K[lo:lo + 512])
+    d_s, _ = dcd_b200.decode_pairs_kpts_depth(kps[lo:lo + 512], k3[lo:lo + 512], rot[lo:lo + 512], K[lo:lo + 512])
+    assert torch.equal(d_s, d_o)
+    assert rel_err(mean[lo:lo + 512], d_o.mean(1)) < 1e-6
+    assert bool(torch.isfinite(mean).all())
