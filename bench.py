@@ -388,7 +388,7 @@ def main():
                                         "CUDA-core roofline (%.1f TFLOP/s) the same number is %.2fx" % (
                                             peaks["source"], 3 * mlp_tflops, fp32_peak, mlp_tflops / fp32_peak),
                          "hbm_gbs": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9, "frac_hbm": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "hbm_bytes_per_object": 198.0e6,
+                         "hbm_bytes_per_object": 198.0e6, "frac_fp32_roofline": mlp_tflops / fp32_peak,
                          "flops_per_object": F_MLP, "avg_launch_ms": mlp_ms / max(n_mlp_launches, 1),
                          "share_of_step": mlp_ms_max / ms},
             "stages": {
