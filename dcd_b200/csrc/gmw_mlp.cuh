@@ -56,4 +56,13 @@ __host__ __device__ inline float2* stat_ptr(float* ws, const WsLayout& L, int ne
     return reinterpret_cast<float2*>(ws + L.stats_off) + (((int64_t)net * L.depth + blk) * 2 + which) * L.stat;
 }
 
+// arguments shared by the forward kernels
+struct MlpArgs {
+    const float* kpts2d;
+    const float* kpts3d;
+    const float* params[2];
+    float* ws;
+    WsLayout L;
+};
+
 }  // namespace dcd

@@ -1,0 +1,600 @@
+// GMW edge-feature MLP forward, inference form: ONE kernel for all 37 layers of a net, the object's
+// activations never leave the chip (sm_100a: thread-block clusters + tcgen05 + TMEM).
+//
+// The layer-wise kernels (gmw_mlp_tc.cu) are bound by HBM: every context norm needs the statistics of the
+// whole object, so each of the 24 normalised layers writes its output and reads it back (198 MB / object).
+// Here a cluster of 8 CTAs owns one (object, net): CTA r holds the edge slice [r*ES, (r+1)*ES) of ALL 128
+// channels on chip for the whole network, and the only thing the CTAs exchange per context norm is the
+// per-channel (mean, M2) partial of their slice, read from each other's shared memory (DSMEM) after a
+// cluster barrier.  Per CTA (ES <= 336 edges, E <= 2688, i.e. up to the reference's n = 73 keypoints):
+//   * residual stream X        : FP32 in shared memory, [ES/4][128 ch] float4            (172 KB)
+//   * layer output (P, Y1, Y2) : FP32 accumulators in tensor memory, columns [0, ES)     (336 of 512 columns);
+//                                every GEMM overwrites its own input sub-tile in place
+//   * weights                  : FP16 hi/lo pairs as the A operand in tensor memory, columns [384, 512),
+//                                reloaded per layer from an L2-resident pre-split image (64 KB / layer)
+//   * B operand                : two 24 KB buffers (hi + lo of a 48-edge sub-tile, MN-major, no swizzle),
+//                                written by the threads that produce the values (thread = channel)
+// Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, Chan-merged
+// statistics); only the order in which the statistics partials are merged differs.
+// HBM traffic: keypoints in, final features out (2.7 MB / object instead of 198 MB).
+#include "gmw_tc_common.cuh"
+
+namespace dcd {
+namespace {
+
+constexpr int FCS = 8;              // CTAs per cluster = edge slices per object
+constexpr int FCONV_WARPS = 12;     // converter warps: 4 TMEM lane quarters x 3 units (16 edges) of a 48-edge sub-tile
+constexpr int FCONV_THREADS = 32 * FCONV_WARPS;
+constexpr int FTHREADS = FCONV_THREADS + 128;   // + 4 service warps: weight loads (all 4), MMA issue (the first)
+constexpr int FSUB = 48;            // edges per MMA sub-tile
+constexpr int FES_MAX = 336;        // edges per CTA
+constexpr uint32_t FT_W = 384;      // tensor-memory columns: D = [0, 336), weights hi = [384, 448), lo = [448, 512)
+constexpr uint32_t FB_SBO = 128;    // B operand: bytes between 8-edge blocks of one 8-channel block
+constexpr uint32_t FB_LBO = 768;    //            bytes between 8-channel blocks (6 edge blocks)
+constexpr uint32_t FB_PART = 16 * FB_LBO;   // 12 KB: hi or lo part of one sub-tile
+
+constexpr size_t SMF_X = 0;
+constexpr size_t SMF_B = SMF_X + (size_t)FES_MAX * CH * sizeof(float);          // [2 buffers]{hi, lo}
+constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [3][128] float4 (mean, M2, count)
+constexpr size_t SMF_OWN = SMF_PART + 3 * CH * sizeof(float4);                  // [2 parities][128] float2
+constexpr size_t SMF_BAR = SMF_OWN + 2 * CH * sizeof(float2);
+constexpr size_t kFusedSmem = SMF_BAR + 128;
+static_assert(kFusedSmem <= 232448, "shared memory budget");
+static_assert(6 * FES_MAX * sizeof(float) <= 4 * FB_PART, "edge features are staged in the operand buffers");
+// mbarriers (8 bytes each, at SMF_BAR)
+enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_COUNT = 6 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 ld_cluster_f2(const void* local, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void conv_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FCONV_THREADS) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// no-swizzle (interleaved) shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t smem_desc_ns(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// (v0, v1) -> packed FP16 pair hp = rn(v) and lp = rn(hp - v) = MINUS the low part (the MMA that consumes the
+// low parts negates B): F2FP + 2 x FHADD (mixed f16/f32 add) + F2FP for two values.
+__device__ __forceinline__ void split2_neg(float v0, float v1, uint32_t& hp, uint32_t& lp) {
+    asm("{\n\t.reg .f16 h0, h1;\n\t.reg .f32 l0, l1;\n\t"
+        "cvt.rn.f16x2.f32 %0, %3, %2;\n\t"
+        "mov.b32 {h0, h1}, %0;\n\t"
+        "sub.rn.f32.f16 l0, h0, %2;\n\t"
+        "sub.rn.f32.f16 l1, h1, %3;\n\t"
+        "cvt.rn.f16x2.f32 %1, l1, l0;\n\t}"
+        : "=&r"(hp), "=r"(lp)
+        : "f"(v0), "f"(v1));
+}
+
+// 16 edges (edge blocks 2u, 2u+1 of the sub-tile) of input channel ch -> FP16 hi / -lo, two 16-byte stores each
+__device__ __forceinline__ void store_unit(unsigned char* b_hi, unsigned char* b_lo, int ch, int u, const float (&v)[16]) {
+    uint32_t hp[8], lp[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split2_neg(v[2 * q], v[2 * q + 1], hp[q], lp[q]);
+    const uint32_t off = (uint32_t)(2 * u) * FB_SBO + (uint32_t)(ch >> 3) * FB_LBO + (uint32_t)(ch & 7) * 16u;
+    *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(b_hi + off + FB_SBO) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+    *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    *reinterpret_cast<uint4*>(b_lo + off + FB_SBO) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+}
+
+// one sub-tile GEMM D[128 x N] = W[128 x 128] . B[128 x N] as 3 x 8 MMAs: Wh.(-(-Bl)), Wl.Bh, Wh.Bh
+__device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int N) {
+    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(CH >> 4) << 24);
+    const uint64_t d_hi = smem_desc_ns(b_hi, FB_LBO, FB_SBO), d_lo = smem_desc_ns(b_lo, FB_LBO, FB_SBO);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+        const uint32_t a = (term == 1) ? a_lo : a_hi;
+        const uint64_t d = (term == 0) ? d_lo : d_hi;
+        const uint32_t id = (term == 0) ? (idesc | (1u << 14)) : idesc;      // bit 14: negate B
+#pragma unroll
+        for (int ks = 0; ks < CH / 16; ++ks) {
+            umma_f16_ts(tmem_d, a + ks * 8, d + (uint64_t)((ks * 2 * FB_LBO) >> 4), id, acc);
+            acc = 1;
+        }
+    }
+}
+
+// Chan merge of (mean, M2, count) with a partial (pm, pM2, pc), pc > 0
+__device__ __forceinline__ void chan_merge(float& mean, float& M2, float& cnt, float pm, float pM2, float pc) {
+    const float tot = cnt + pc, delta = pm - mean;
+    mean += delta * (pc / tot);
+    M2 += pM2 + delta * delta * (cnt * pc / tot);
+    cnt = tot;
+}
+
+}  // namespace
+
+// Pre-split weight image of one matrix: [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1)
+// of scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
+__global__ void __launch_bounds__(256) tc_weight_image_kernel(const float* __restrict__ p4, const float* __restrict__ p6,
+                                                              int depth, const float2* __restrict__ scales,
+                                                              uint32_t* __restrict__ img) {
+    const int m = blockIdx.x;
+    const int which = m % 3, blk = (m / 3) % depth, net = m / (3 * depth);
+    const int cin = net == 0 ? 4 : 6;
+    const float* Wt = (net == 0 ? p4 : p6) + blob_w(cin, blk, which);
+    const float scale = scales[m].x;
+    uint32_t* out = img + (size_t)m * CH * CH;
+    for (int idx = threadIdx.x; idx < CH * 64; idx += 256) {
+        const int row = idx & 127, c = idx >> 7;
+        const float w0 = Wt[(2 * c) * CH + row] * scale, w1 = Wt[(2 * c + 1) * CH + row] * scale;
+        const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
+        const __half l0 = __float2half_rn(w0 - __half2float(h0)), l1 = __float2half_rn(w1 - __half2float(h1));
+        out[row * CH + c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        out[row * CH + 64 + c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+}
+
+namespace {
+
+__global__ void __cluster_dims__(FCS, 1, 1) __launch_bounds__(FTHREADS, 1)
+mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* __restrict__ wimg) {
+    const WsLayout& L = a.L;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
+    const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+    const int ch = 32 * quarter + lane;                      // this thread's channel = TMEM lane = weight row
+    const uint32_t rank = cluster_ctarank();
+    const int E = L.E, EP = L.EP, depth = L.depth;
+    const int ES = 16 * ((E + 127) / 128);                   // edges per CTA (8 * ES == EP)
+    const int nsub = (ES + FSUB - 1) / FSUB;
+    const int nphase = 3 * depth;
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float4* Xs = reinterpret_cast<float4*>(smem + SMF_X);
+    unsigned char* Bbuf = smem + SMF_B;
+    float4* part_s = reinterpret_cast<float4*>(smem + SMF_PART);
+    float2* own_s = reinterpret_cast<float2*>(smem + SMF_OWN);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMF_BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMF_BAR + 8 * BAR_COUNT);
+
+    if (tid == 0) {
+        mbar_init(bar + BAR_FULL0, FCONV_WARPS);
+        mbar_init(bar + BAR_FULL1, FCONV_WARPS);
+        mbar_init(bar + BAR_DONE0, 1);
+        mbar_init(bar + BAR_DONE1, 1);
+        mbar_init(bar + BAR_PDONE, 1);
+        mbar_init(bar + BAR_WREADY, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * quarter) << 16);
+    const int64_t nitems = L.N * 2;
+    const int64_t item0 = cluster_id_x(), item_step = cluster_count_x();
+
+    if (warp >= FCONV_WARPS) {
+        // =====================================================================================================
+        // service warps: stream the layers' weight images into tensor memory; the first one issues the MMAs
+        // =====================================================================================================
+        uint32_t wr[64];
+        auto w_src = [&](int mat) { return reinterpret_cast<const uint4*>(wimg + ((size_t)mat * CH + ch) * CH); };
+        auto w_load = [&](const uint4* src, int half) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint4 v = __ldg(src + 16 * half + i);
+                wr[4 * i] = v.x; wr[4 * i + 1] = v.y; wr[4 * i + 2] = v.z; wr[4 * i + 3] = v.w;
+            }
+        };
+        auto w_store = [&](int half) {
+            uint32_t t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = wr[i];
+            tmem_st32(t_lane + FT_W + 64 * half, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = wr[32 + i];
+            tmem_st32(t_lane + FT_W + 64 * half + 32, t);
+        };
+        auto w_publish = [&]() {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + BAR_WREADY);
+        };
+        uint32_t g = 0;                                       // running sub-tile step: operand buffer = g & 1
+        uint32_t fpar = 0, wpar = 0, ppar = 0;                // parities: full[2] (bits), wready, pdone
+        if (item0 < nitems) {
+            const uint4* src = w_src((int)(item0 & 1) * nphase);
+            w_load(src, 0);
+            w_store(0);
+            w_load(src, 1);
+            w_store(1);
+            w_publish();
+        }
+        for (int64_t item = item0; item < nitems; item += item_step) {
+            const int mat_base = (int)(item & 1) * nphase;
+            for (int ph = 0; ph < nphase; ++ph) {
+                if (warp == FCONV_WARPS) {
+                    mbar_wait(bar + BAR_WREADY, wpar);
+                    tc_fence_after();
+                    for (int s = 0; s < nsub; ++s, ++g) {
+                        const uint32_t b = g & 1u;
+                        mbar_wait(bar + BAR_FULL0 + b, (fpar >> b) & 1u);
+                        fpar ^= 1u << b;
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t b_hi = smem_u32(Bbuf) + b * 2 * FB_PART;
+                            issue_sub_gemm(tmem_base + FSUB * s, tmem_base + FT_W, tmem_base + FT_W + 64, b_hi, b_hi + FB_PART,
+                                           min(FSUB, ES - FSUB * s));
+                            umma_commit(bar + BAR_DONE0 + b);
+                            if (s == nsub - 1) umma_commit(bar + BAR_PDONE);
+                        }
+                        __syncwarp();
+                    }
+                }
+                wpar ^= 1u;
+                // next layer's weights: first half fetched while this layer's last MMAs drain
+                const bool last_ph = ph + 1 == nphase;
+                const bool more = !last_ph || item + item_step < nitems;
+                if (more) {
+                    const uint4* src = w_src(last_ph ? (int)((item + item_step) & 1) * nphase : mat_base + ph + 1);
+                    w_load(src, 0);
+                    mbar_wait(bar + BAR_PDONE, ppar);
+                    tc_fence_after();
+                    w_store(0);
+                    w_load(src, 1);
+                    w_store(1);
+                    w_publish();
+                } else {
+                    mbar_wait(bar + BAR_PDONE, ppar);
+                }
+                ppar ^= 1u;
+                if (ph % 3 != 0) {                            // the converters' statistics exchange of this layer
+                    cluster_arrive();
+                    cluster_wait();
+                }
+            }
+        }
+    } else {
+        // =====================================================================================================
+        // converter warps: thread = channel; units of 16 edges; produce the B operands, consume the accumulators
+        // =====================================================================================================
+        const int wg = warp >> 2;                             // unit inside a sub-tile
+        const int e_base = (int)rank * ES;
+        const int valid = max(0, min(ES, E - e_base));
+        uint32_t g = 0;                                       // running sub-tile step (same sequence as the MMA warp)
+        uint32_t par = 0, pend = 0;                           // per operand buffer: next wait parity, MMA in flight
+        auto wait_buf = [&](uint32_t b) {
+            if ((pend >> b) & 1u) {
+                mbar_wait(bar + BAR_DONE0 + b, (par >> b) & 1u);
+                par ^= 1u << b;
+                pend &= ~(1u << b);
+                tc_fence_after();
+            }
+        };
+        uint32_t xpar = 0;                                    // parity of the statistics exchange slot
+
+        for (int64_t item = item0; item < nitems; item += item_step) {
+            const int64_t obj = item >> 1;
+            const int net = (int)(item & 1);
+            const int cin = net == 0 ? 4 : 6;
+            const float* __restrict__ prm = a.params[net];
+            const int mat_base = net * nphase;
+
+            // ---- edge features of this slice, staged in the (idle) operand buffers: f_s[6][ES]
+            wait_buf(0);
+            wait_buf(1);
+            conv_sync();
+            float* f_s = reinterpret_cast<float*>(Bbuf);
+            if (tid < ES) {
+                const int e = e_base + tid;
+                int i, j;
+                decode_edge(e < E ? e : E - 1, L.n, i, j);
+                float f[6];
+                if (net == 0) {
+                    const float2 pi = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + i) * 2));
+                    const float2 pj = __ldg(reinterpret_cast<const float2*>(a.kpts2d + (obj * L.n + j) * 2));
+                    f[0] = pi.x; f[1] = pi.y; f[2] = pj.x; f[3] = pj.y; f[4] = 0.f; f[5] = 0.f;
+                } else {
+                    const float* pi = a.kpts3d + (obj * L.n + i) * 3;
+                    const float* pj = a.kpts3d + (obj * L.n + j) * 3;
+                    f[0] = __ldg(pi); f[1] = __ldg(pi + 1); f[2] = __ldg(pi + 2);
+                    f[3] = __ldg(pj); f[4] = __ldg(pj + 1); f[5] = __ldg(pj + 2);
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) f_s[r * ES + tid] = f[r];
+            }
+            conv_sync();
+            // ---- conv_in: X0 = W_in . f + b_in   (the features are warp-wide broadcasts)
+            {
+                float wq[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + ch) : 0.f;
+                const float b = __ldg(prm + blob_in_b(cin) + ch);
+                for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = col0 + 4 * q4 + i;
+                            float acc = b;
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) acc = fmaf(wq[r], f_s[r * ES + e], acc);
+                            x[i] = (e < valid) ? acc : 0.f;
+                        }
+                        Xs[((col0 >> 2) + q4) * CH + ch] = make_float4(x[0], x[1], x[2], x[3]);
+                    }
+                }
+            }
+            conv_sync();                                      // the features are consumed: operand buffers free
+
+            float un_in = 0.f, b_in = 0.f;                    // scale/bias of the matrix that produced the current D
+            float2 st = make_float2(0.f, 1.f);                // (mean, rstd) of the current D's context norm
+            for (int ph = 0; ph < nphase; ++ph) {
+                const int blk = ph / 3, kind = ph - 3 * blk;  // 0 preconv, 1 conv1, 2 conv2
+                const float un_out = __ldg(scales + mat_base + ph).y;
+                const float b_out = __ldg(prm + blob_b(cin, blk, kind) + ch);
+                // input transform of this layer as one FMA on the raw accumulator: kind 1: + bias;
+                // kinds 0, 2: context norm of the producing layer folded in ((d*un + b - mean) * rstd)
+                const float a_in = (kind == 1) ? un_in : un_in * st.y;
+                const float c_in = (kind == 1) ? b_in : (b_in - st.x) * st.y;
+                // statistics of this layer's output as shifted sums around K (K = mean of the first unit)
+                float K = 0.f, s1 = 0.f, s2 = 0.f, cnt = 0.f, bK = b_out;
+                const uint32_t g0 = g;
+
+                auto stats_unit = [&](int sp) {
+                    wait_buf((g0 + (uint32_t)sp) & 1u);
+                    const int col0 = FSUB * sp + 16 * wg;
+                    const int nv = min(16, valid - col0);
+                    if (nv <= 0) return;
+                    float v[16];
+                    tmem_ld16(t_lane + col0, v);
+                    if (cnt == 0.f) {                         // first unit: choose the shift
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = fmaf(v[i], un_out, b_out);
+                            if (i < nv) sum += v[i];
+                        }
+                        K = sum / (float)nv;
+                        bK = b_out - K;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < nv) {
+                                const float d = v[i] - K;
+                                s1 += d;
+                                s2 = fmaf(d, d, s2);
+                            }
+                    } else if (nv == 16) {
+                        float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float d = fmaf(v[i], un_out, bK);
+                            t1[i & 3] += d;
+                            t2[i & 3] = fmaf(d, d, t2[i & 3]);
+                        }
+                        s1 += (t1[0] + t1[1]) + (t1[2] + t1[3]);
+                        s2 += (t2[0] + t2[1]) + (t2[2] + t2[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < nv) {
+                                const float d = fmaf(v[i], un_out, bK);
+                                s1 += d;
+                                s2 = fmaf(d, d, s2);
+                            }
+                    }
+                    cnt += (float)nv;
+                };
+
+                if (nsub < 2) {                               // (with >= 2 sub-tiles the buffer waits below imply it)
+                    wait_buf(0);
+                    wait_buf(1);
+                }
+                for (int s = 0; s < nsub; ++s, ++g) {
+                    const uint32_t b = g & 1u;
+                    wait_buf(b);
+                    unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
+                    const int col0 = FSUB * s + 16 * wg;
+                    if (col0 < ES) {
+                        float v[16];
+                        if (kind == 0) {
+                            float4* Xp = Xs + (col0 >> 2) * CH + ch;
+                            float4 x4[4];
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                            if (ph > 0) {
+                                tmem_ld16(t_lane + col0, v);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_in, c_in), 0.f);
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
+                                }
+                                if (col0 + 16 > valid) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+                                        if (col0 + i >= valid) v[i] = 0.f;
+                                }
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4)
+                                    Xp[q4 * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    v[4 * q4] = x4[q4].x; v[4 * q4 + 1] = x4[q4].y; v[4 * q4 + 2] = x4[q4].z; v[4 * q4 + 3] = x4[q4].w;
+                                }
+                            }
+                        } else {
+                            tmem_ld16(t_lane + col0, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a_in, c_in);
+                        }
+                        store_unit(b_hi, b_hi + FB_PART, ch, wg, v);
+                    }
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar + BAR_FULL0 + b);
+                    pend |= 1u << b;
+                    if (kind != 0 && s > 0) stats_unit(s - 1);
+                }
+                if (kind != 0) {
+                    stats_unit(nsub - 1);
+                    // ---- context-norm statistics: merge the 3 unit streams, publish, cluster barrier, merge the 8 slices
+                    {
+                        float m = 0.f, M2 = 0.f;
+                        if (cnt > 0.f) {
+                            m = K + s1 / cnt;
+                            M2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+                        }
+                        part_s[wg * CH + ch] = make_float4(m, M2, cnt, 0.f);
+                    }
+                    conv_sync();
+                    if (wg == 0) {
+                        float m = 0.f, M2 = 0.f, c = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const float4 p = part_s[q * CH + ch];
+                            if (p.z > 0.f) chan_merge(m, M2, c, p.x, p.y, p.z);
+                        }
+                        own_s[xpar * CH + ch] = make_float2(m, M2);
+                    }
+                    cluster_arrive();
+                    cluster_wait();
+                    float m = 0.f, M2 = 0.f, c = 0.f;
+#pragma unroll
+                    for (int r = 0; r < FCS; ++r) {
+                        const float2 p = ld_cluster_f2(own_s + xpar * CH + ch, (uint32_t)r);
+                        const float pc = (float)max(0, min(ES, E - r * ES));
+                        if (pc > 0.f) chan_merge(m, M2, c, p.x, p.y, pc);
+                    }
+                    const float var = M2 / (float)(E - 1);
+                    st = make_float2(m, 1.0f / sqrtf(var + 1e-3f));
+                    xpar ^= 1u;
+                }
+                un_in = un_out;
+                b_in = b_out;
+            }
+
+            // ---- final features x = relu(cn(Y2)) + X -> global, channel-major [obj][128][EP]
+            {
+                const float a_in = un_in * st.y, c_in = (b_in - st.x) * st.y;
+                float* G = act_ptr(a.ws, L, net, 0, SLOT_X) + obj * (int64_t)CH * EP + (int64_t)ch * EP + e_base;
+                for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
+                    float v[16];
+                    const float4* Xp = Xs + (col0 >> 2) * CH + ch;
+                    float4 x4[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                    tmem_ld16(t_lane + col0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_in, c_in), 0.f);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
+                    }
+                    if (col0 + 16 > valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (col0 + i >= valid) v[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        *reinterpret_cast<float4*>(G + col0 + 4 * q4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                }
+                tc_fence_before();                            // the next item's MMAs overwrite these columns
+            }
+        }
+    }
+    // nobody may leave while a peer can still read its statistics slot
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool gmw_fused_supported(int n) {
+    const int E = n * (n - 1) / 2;
+    return 16 * ((E + 127) / 128) <= FES_MAX;
+}
+
+size_t gmw_fused_image_bytes(int depth) { return (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t); }
+
+// Runs both nets of all objects; the final features land in SLOT_X of the (inference-layout) workspace.
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, const float2* scales,
+                         uint32_t* wimg, cudaStream_t st) {
+    const int depth = a.L.depth;
+    tc_weight_image_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales, wimg);
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(FCS * 64);
+        cfg.blockDim = dim3(FTHREADS);
+        cfg.dynamicSmemBytes = kFusedSmem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = FCS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, mlp_fused_kernel, &cfg) != cudaSuccess || nc <= 0) {
+            cudaGetLastError();
+            nc = device_sm_count() / FCS - 2;
+            if (nc < 1) nc = 1;
+        }
+        max_clusters = nc;
+    }
+    const int64_t nitems = a.L.N * 2;
+    const int nclusters = (int)(nitems < max_clusters ? nitems : max_clusters);
+    mlp_fused_kernel<<<FCS * nclusters, FTHREADS, kFusedSmem, st>>>(a, scales, wimg);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

@@ -17,17 +17,10 @@
 //     output, which never leaves the SM;
 //   * the epilogue reads D with tcgen05.ld (32 lanes x 32 columns per warp): a thread owns one output
 //     channel, so bias, context-norm statistics and the split for the next GEMM need no shuffles.
+#include <cstdlib>
 #include "gmw_tc_common.cuh"
 
 namespace dcd {
-
-struct MlpArgs {
-    const float* kpts2d;
-    const float* kpts3d;
-    const float* params[2];
-    float* ws;
-    WsLayout L;
-};
 
 namespace {
 
@@ -398,7 +391,9 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// Final features of both nets -> reg_weights (same arithmetic as the CUDA-core path's kernel).
+// Final features of both nets -> reg_weights.  FINAL: SLOT_X already holds the final features (fused forward);
+// otherwise the last block's context norm + ReLU + residual is applied on the fly.
+template <bool FINAL>
 __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* __restrict__ reg_w,
                                                               float* __restrict__ feat4, float* __restrict__ feat6) {
     const WsLayout& L = a.L;
@@ -407,23 +402,27 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
     const int64_t obj = blockIdx.x / nb;
     const int e = (blockIdx.x % nb) * 256 + threadIdx.x;
     __shared__ float2 stat_s[2][CH];
-    {
+    if (!FINAL) {
         const int net = threadIdx.x >> 7, c = threadIdx.x & 127;
         stat_s[net][c] = merge_cn_stats(stat_ptr(a.ws, L, net, last, 1) + obj * (int64_t)L.T * CH, c, L.T, E);
+        __syncthreads();
     }
-    __syncthreads();
     if (e >= E) return;
     const int64_t off = obj * (int64_t)CH * EP + e;
     const float* Y4 = act_ptr(a.ws, L, 0, last, SLOT_Y2) + off;
-    const float* X4 = act_ptr(a.ws, L, 0, last, SLOT_X) + off;
+    const float* X4 = act_ptr(a.ws, L, 0, FINAL ? 0 : last, SLOT_X) + off;
     const float* Y6 = act_ptr(a.ws, L, 1, last, SLOT_Y2) + off;
-    const float* X6 = act_ptr(a.ws, L, 1, last, SLOT_X) + off;
+    const float* X6 = act_ptr(a.ws, L, 1, FINAL ? 0 : last, SLOT_X) + off;
+    auto feature = [&](const float* Y, const float* X, const float2 s, int c) {
+        if (FINAL) return X[(int64_t)c * EP];
+        return fmaxf((Y[(int64_t)c * EP] - s.x) * s.y, 0.f) + X[(int64_t)c * EP];
+    };
     float n4 = 0.f, n6 = 0.f;
 #pragma unroll 4
     for (int c = 0; c < CH; ++c) {
-        const float2 s4 = stat_s[0][c], s6 = stat_s[1][c];
-        const float x4 = fmaxf((Y4[(int64_t)c * EP] - s4.x) * s4.y, 0.f) + X4[(int64_t)c * EP];
-        const float x6 = fmaxf((Y6[(int64_t)c * EP] - s6.x) * s6.y, 0.f) + X6[(int64_t)c * EP];
+        const float2 s4 = FINAL ? make_float2(0.f, 0.f) : stat_s[0][c], s6 = FINAL ? make_float2(0.f, 0.f) : stat_s[1][c];
+        const float x4 = feature(Y4, X4, s4, c);
+        const float x6 = feature(Y6, X6, s6, c);
         n4 = fmaf(x4, x4, n4);
         n6 = fmaf(x6, x6, n6);
         if (feat4 != nullptr) feat4[(obj * CH + c) * (int64_t)E + e] = x4;
@@ -434,9 +433,9 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
     float a2 = 0.f, c2 = 0.f, ac = 0.f;
 #pragma unroll 4
     for (int c = 0; c < CH; ++c) {
-        const float2 s4 = stat_s[0][c], s6 = stat_s[1][c];
-        const float x4 = fmaxf((Y4[(int64_t)c * EP] - s4.x) * s4.y, 0.f) + X4[(int64_t)c * EP];
-        const float x6 = fmaxf((Y6[(int64_t)c * EP] - s6.x) * s6.y, 0.f) + X6[(int64_t)c * EP];
+        const float2 s4 = FINAL ? make_float2(0.f, 0.f) : stat_s[0][c], s6 = FINAL ? make_float2(0.f, 0.f) : stat_s[1][c];
+        const float x4 = feature(Y4, X4, s4, c);
+        const float x6 = feature(Y6, X6, s6, c);
         const float av = __fdiv_rn(x4, n4), cv = __fdiv_rn(x6, n6);
         a2 = fmaf(av, av, a2);
         c2 = fmaf(cv, cv, c2);
@@ -450,8 +449,23 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
 }  // namespace
 
 // bytes appended to the MLP workspace for the per-matrix FP16 scales (scale, 1/scale)
-size_t tc_weight_image_bytes(int depth) {
-    return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256;
+bool gmw_fused_supported(int n);
+size_t gmw_fused_image_bytes(int depth);
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, const float2* scales,
+                         uint32_t* wimg, cudaStream_t st);
+
+static size_t tc_scales_bytes(int depth) { return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256; }
+// bytes appended to the MLP workspace: per-matrix FP16 scales (scale, 1/scale) + the pre-split weight image
+// of the fused forward
+size_t tc_weight_image_bytes(int depth) { return tc_scales_bytes(depth) + gmw_fused_image_bytes(depth); }
+
+// DCD_B200_LAYERWISE=1 forces the layer-wise kernels also for inference (A/B measurements, cross-checks)
+static bool force_layerwise() {
+    static const int v = [] {
+        const char* e = getenv("DCD_B200_LAYERWISE");
+        return (e != nullptr && e[0] == '1') ? 1 : 0;
+    }();
+    return v != 0;
 }
 
 int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
@@ -467,6 +481,16 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     float2* scales = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ws) +
                                                (((size_t)a.L.total * sizeof(float) + 255) / 256) * 256);
     tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
+    const unsigned g2 = (unsigned)(((a.L.E + 255) / 256) * N);
+    if (!save && gmw_fused_supported(n) && !force_layerwise()) {
+        // inference: whole network on chip, one kernel (gmw_mlp_fused.cu)
+        uint32_t* wimg = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth));
+        const int rc = launch_gmw_fused_fwd(a, params4, params6, scales, wimg, st);
+        if (rc != DCD_OK) return rc;
+        gmw_edge_weight_kernel<true><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
+        DCD_CHECK_LAUNCH();
+        return DCD_OK;
+    }
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
@@ -480,8 +504,7 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
         if (blk + 1 < depth) mlp_tc_kernel<MODE_CA><<<grid, TC_THREADS, kTcSmem, st>>>(a, blk + 1, scales);
     }
     DCD_CHECK_LAUNCH();
-    const unsigned g2 = (unsigned)(((a.L.E + 255) / 256) * N);
-    gmw_edge_weight_kernel<<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
+    gmw_edge_weight_kernel<false><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
     DCD_CHECK_LAUNCH();
     return DCD_OK;
 }

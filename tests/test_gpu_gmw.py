@@ -173,6 +173,27 @@ def test_weight_gradients_full_size_vs_reference_fixture(golden):
             assert float(mine[k].abs().max()) < 1e-4 * gmax, k
 
 
+@pytest.mark.parametrize("n,depth,N", [(73, 12, 5), (60, 3, 3), (8, 2, 9), (17, 1, 1), (74, 2, 2)])
+def test_fused_inference_forward_agrees_with_layerwise_training_forward(n, depth, N):
+    """Inference (no grad) runs the whole network in one cluster kernel with the activations on chip; the
+    training forward runs layer by layer through HBM.  Same arithmetic, different merge order of the context-norm
+    partials: the two must agree to FP32 rounding.  n = 74 exceeds the on-chip capacity and takes the layer-wise
+    kernels in both modes."""
+    ob = synth.make_objects(N=N, n=n, seed=900 + n)
+    sd = O.random_state_dict(50 + n, depth=depth)
+    model = make_model(sd, depth)
+    k2, k3 = cu(ob.kps_norm, ob.kps_3d)
+    with torch.no_grad():
+        w_inf, _ = model(k2, k3)
+    w_trn, _ = model(k2, k3)
+    assert w_trn.requires_grad and not w_inf.requires_grad
+    assert bool(torch.isfinite(w_inf).all())
+    assert rel_err(w_inf, w_trn.detach()) < 2e-5, (n, depth)
+    with torch.no_grad():
+        w_again, _ = model(k2, k3)
+    assert torch.equal(w_inf, w_again)                    # deterministic
+
+
 def test_state_dict_round_trip():
     sd = O.random_state_dict(3)
     model = make_model(sd)
