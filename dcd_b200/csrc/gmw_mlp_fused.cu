@@ -35,14 +35,14 @@ constexpr uint32_t FB_PART = 16 * FB_LBO;   // 12 KB: hi or lo part of one sub-t
 
 constexpr size_t SMF_X = 0;
 constexpr size_t SMF_B = SMF_X + (size_t)FES_MAX * CH * sizeof(float);          // [2 buffers]{hi, lo}
-constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [3][128] float4 (mean, M2, count)
+constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [3][128] float2 (mean, M2) + count tables
 constexpr size_t SMF_OWN = SMF_PART + 3 * CH * sizeof(float4);                  // [2 parities][128] float2
 constexpr size_t SMF_BAR = SMF_OWN + 2 * CH * sizeof(float2);
 constexpr size_t kFusedSmem = SMF_BAR + 128;
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 static_assert(6 * FES_MAX * sizeof(float) <= 4 * FB_PART, "edge features are staged in the operand buffers");
 // mbarriers (8 bytes each, at SMF_BAR)
-enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_COUNT = 6 };
+enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_XCHG = 6, BAR_COUNT = 7 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -90,6 +90,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// the same load split into issue and wait, so that its latency can be covered by independent work
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// packed FP32 pair arithmetic (sm_100 FFMA2 / FADD2): one issue slot for two elements
+__device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {   // d = a * b + c
+    asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %5};\n\t"
+        "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fsq2_acc(float& s0, float& s1, float d0, float d1) {                      // s += d * d
+    asm("{\n\t.reg .b64 d, s;\n\tmov.b64 d, {%2, %3};\n\tmov.b64 s, {%0, %1};\n\t"
+        "fma.rn.f32x2 s, d, d, s;\n\tmov.b64 {%0, %1}, s;\n\t}"
+        : "+f"(s0), "+f"(s1) : "f"(d0), "f"(d1));
+}
+__device__ __forceinline__ void fadd2_acc(float& s0, float& s1, float d0, float d1) {                     // s += d
+    asm("{\n\t.reg .b64 d, s;\n\tmov.b64 d, {%2, %3};\n\tmov.b64 s, {%0, %1};\n\t"
+        "add.rn.f32x2 s, s, d;\n\tmov.b64 {%0, %1}, s;\n\t}"
+        : "+f"(s0), "+f"(s1) : "f"(d0), "f"(d1));
+}
+
+// cluster-scope mbarrier signalling: arrive on the barrier of CTA `rank`, wait on the local one
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "XWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XWAIT_DONE;\n\t"
+        "bra XWAIT_LOOP;\n\t"
+        "XWAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // no-swizzle (interleaved) shared-memory matrix descriptor
@@ -140,14 +193,6 @@ __device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, u
     }
 }
 
-// Chan merge of (mean, M2, count) with a partial (pm, pM2, pc), pc > 0
-__device__ __forceinline__ void chan_merge(float& mean, float& M2, float& cnt, float pm, float pM2, float pc) {
-    const float tot = cnt + pc, delta = pm - mean;
-    mean += delta * (pc / tot);
-    M2 += pM2 + delta * delta * (cnt * pc / tot);
-    cnt = tot;
-}
-
 }  // namespace
 
 // Pre-split weight image of one matrix: [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1)
@@ -189,7 +234,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* Xs = reinterpret_cast<float4*>(smem + SMF_X);
     unsigned char* Bbuf = smem + SMF_B;
-    float4* part_s = reinterpret_cast<float4*>(smem + SMF_PART);
+    float2* part2_s = reinterpret_cast<float2*>(smem + SMF_PART);            // [3][128] (mean, M2) per unit stream
+    float2* tab_s = reinterpret_cast<float2*>(smem + SMF_PART + 3 * CH * sizeof(float2));   // counts, see below
+    float2* stat_s = tab_s + 16;                                                    // [128] (mean, rstd) of the current context norm
     float2* own_s = reinterpret_cast<float2*>(smem + SMF_OWN);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMF_BAR);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMF_BAR + 8 * BAR_COUNT);
@@ -201,12 +248,26 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
         mbar_init(bar + BAR_DONE1, 1);
         mbar_init(bar + BAR_PDONE, 1);
         mbar_init(bar + BAR_WREADY, 4);
+        mbar_init(bar + BAR_XCHG, FCS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // statistics merge weights: tab_s[q] = (n_q, n_q / n_cta) for the 3 unit streams of this CTA (q = 0..2),
+    // tab_s[4 + r] = (n_r, n_r / E) for the 8 slices of the object
+    if (tid < 3) {
+        const int vld = max(0, min(ES, E - (int)rank * ES));
+        int nq = 0;
+        for (int col0 = 16 * tid; col0 < ES; col0 += FSUB) nq += max(0, min(16, vld - col0));
+        tab_s[tid] = make_float2((float)nq, vld > 0 ? (float)nq / (float)vld : 0.f);
+    } else if (tid >= 4 && tid < 4 + FCS) {
+        const int nr = max(0, min(ES, E - (tid - 4) * ES));
+        tab_s[tid] = make_float2((float)nr, (float)nr / (float)E);
     }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    cluster_arrive();                                       // peers' mbarriers are initialised before any remote arrive
+    cluster_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const int64_t nitems = L.N * 2;
@@ -288,10 +349,6 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     mbar_wait(bar + BAR_PDONE, ppar);
                 }
                 ppar ^= 1u;
-                if (ph % 3 != 0) {                            // the converters' statistics exchange of this layer
-                    cluster_arrive();
-                    cluster_wait();
-                }
             }
         }
     } else {
@@ -312,6 +369,8 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
             }
         };
         uint32_t xpar = 0;                                    // parity of the statistics exchange slot
+        const float inv_cnt_wg = tab_s[wg].x > 0.f ? 1.0f / tab_s[wg].x : 0.f;
+        const float inv_em1 = 1.0f / (float)(E - 1);
 
         for (int64_t item = item0; item < nitems; item += item_step) {
             const int64_t obj = item >> 1;
@@ -378,26 +437,27 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                 // kinds 0, 2: context norm of the producing layer folded in ((d*un + b - mean) * rstd)
                 const float a_in = (kind == 1) ? un_in : un_in * st.y;
                 const float c_in = (kind == 1) ? b_in : (b_in - st.x) * st.y;
-                // statistics of this layer's output as shifted sums around K (K = mean of the first unit)
-                float K = 0.f, s1 = 0.f, s2 = 0.f, cnt = 0.f, bK = b_out;
+                // statistics of this layer's output as shifted sums around K (K = mean of this thread's first unit)
+                float K = 0.f, s1 = 0.f, s2 = 0.f, bK = b_out;
+                bool have_K = false;
                 const uint32_t g0 = g;
+                const bool reads_d = ph > 0;
+                const bool stats = kind != 0;
 
-                auto stats_unit = [&](int sp) {
-                    wait_buf((g0 + (uint32_t)sp) & 1u);
-                    const int col0 = FSUB * sp + 16 * wg;
-                    const int nv = min(16, valid - col0);
+                // statistics of one unit from its raw accumulators
+                auto stats_math = [&](const uint32_t (&raw)[16], int sp) {
+                    const int nv = min(16, valid - (FSUB * sp + 16 * wg));
                     if (nv <= 0) return;
-                    float v[16];
-                    tmem_ld16(t_lane + col0, v);
-                    if (cnt == 0.f) {                         // first unit: choose the shift
-                        float sum = 0.f;
+                    if (!have_K) {                            // first unit: choose the shift
+                        float v[16], sum = 0.f;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            v[i] = fmaf(v[i], un_out, b_out);
+                            v[i] = fmaf(__uint_as_float(raw[i]), un_out, b_out);
                             if (i < nv) sum += v[i];
                         }
                         K = sum / (float)nv;
                         bK = b_out - K;
+                        have_K = true;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (i < nv) {
@@ -408,10 +468,14 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     } else if (nv == 16) {
                         float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float d = fmaf(v[i], un_out, bK);
-                            t1[i & 3] += d;
-                            t2[i & 3] = fmaf(d, d, t2[i & 3]);
+                        for (int i = 0; i < 16; i += 4) {
+                            float d0, d1, d2, d3;
+                            ffma2_bc(d0, d1, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]), un_out, bK);
+                            ffma2_bc(d2, d3, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]), un_out, bK);
+                            fadd2_acc(t1[0], t1[1], d0, d1);
+                            fadd2_acc(t1[2], t1[3], d2, d3);
+                            fsq2_acc(t2[0], t2[1], d0, d1);
+                            fsq2_acc(t2[2], t2[3], d2, d3);
                         }
                         s1 += (t1[0] + t1[1]) + (t1[2] + t1[3]);
                         s2 += (t2[0] + t2[1]) + (t2[2] + t2[3]);
@@ -419,37 +483,52 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (i < nv) {
-                                const float d = fmaf(v[i], un_out, bK);
+                                const float d = fmaf(__uint_as_float(raw[i]), un_out, bK);
                                 s1 += d;
                                 s2 = fmaf(d, d, s2);
                             }
                     }
-                    cnt += (float)nv;
                 };
 
-                if (nsub < 2) {                               // (with >= 2 sub-tiles the buffer waits below imply it)
+                if (nsub < 3) {                               // (with >= 3 sub-tiles the buffer waits of the pipeline imply it)
                     wait_buf(0);
                     wait_buf(1);
                 }
+                // Software pipeline over the sub-tiles: the accumulators of the NEXT unit to convert (cv) and of the
+                // unit whose statistics are due (sv, two steps behind: its MMA is known complete when its operand
+                // buffer comes free) are in flight from tensor memory while the current unit is being processed.
+                uint32_t cv[16], sv[16];
+                const bool unit0 = 16 * wg < ES;
+                if (reads_d && unit0) tmem_ld16_issue(t_lane + 16 * wg, cv);
                 for (int s = 0; s < nsub; ++s, ++g) {
                     const uint32_t b = g & 1u;
                     wait_buf(b);
                     unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
                     const int col0 = FSUB * s + 16 * wg;
-                    if (col0 < ES) {
-                        float v[16];
+                    const bool active = col0 < ES;
+                    const bool do_stats = stats && s >= 2 && valid > col0 - 2 * FSUB;
+                    float v[16];
+                    float4* Xp = Xs + (col0 >> 2) * CH + ch;
+                    float4 x4[4];
+                    if (active && kind == 0) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                    }
+                    if (reads_d && active) tmem_ld16_wait(cv);
+                    if (do_stats) tmem_ld16_issue(t_lane + col0 - 2 * FSUB, sv);
+                    if (active) {
                         if (kind == 0) {
-                            float4* Xp = Xs + (col0 >> 2) * CH + ch;
-                            float4 x4[4];
+                            if (reads_d) {
 #pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
-                            if (ph > 0) {
-                                tmem_ld16(t_lane + col0, v);
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_in, c_in), 0.f);
+                                for (int i = 0; i < 16; i += 2) {
+                                    ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
+                                    v[i] = fmaxf(v[i], 0.f);
+                                    v[i + 1] = fmaxf(v[i + 1], 0.f);
+                                }
 #pragma unroll
                                 for (int q4 = 0; q4 < 4; ++q4) {
-                                    v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
+                                    fadd2_acc(v[4 * q4], v[4 * q4 + 1], x4[q4].x, x4[q4].y);
+                                    fadd2_acc(v[4 * q4 + 2], v[4 * q4 + 3], x4[q4].z, x4[q4].w);
                                 }
                                 if (col0 + 16 > valid) {
 #pragma unroll
@@ -466,9 +545,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                                 }
                             }
                         } else {
-                            tmem_ld16(t_lane + col0, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a_in, c_in);
+                            for (int i = 0; i < 16; i += 2)
+                                ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
                         }
                         store_unit(b_hi, b_hi + FB_PART, ch, wg, v);
                     }
@@ -477,40 +556,70 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + BAR_FULL0 + b);
                     pend |= 1u << b;
-                    if (kind != 0 && s > 0) stats_unit(s - 1);
+                    if (do_stats) tmem_ld16_wait(sv);
+                    if (reads_d && s + 1 < nsub && col0 + FSUB < ES) tmem_ld16_issue(t_lane + col0 + FSUB, cv);
+                    if (do_stats) stats_math(sv, s - 2);
                 }
-                if (kind != 0) {
-                    stats_unit(nsub - 1);
-                    // ---- context-norm statistics: merge the 3 unit streams, publish, cluster barrier, merge the 8 slices
-                    {
-                        float m = 0.f, M2 = 0.f;
-                        if (cnt > 0.f) {
-                            m = K + s1 / cnt;
-                            M2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+                if (stats) {
+                    // the last two sub-tiles' statistics: the first overlaps the drain of the last MMAs
+                    const int spa = nsub - 2, spb = nsub - 1;
+                    if (spa >= 0) {
+                        wait_buf((g0 + (uint32_t)spa) & 1u);
+                        if (valid > FSUB * spa + 16 * wg) {
+                            tmem_ld16_issue(t_lane + FSUB * spa + 16 * wg, sv);
+                            tmem_ld16_wait(sv);
+                            stats_math(sv, spa);
                         }
-                        part_s[wg * CH + ch] = make_float4(m, M2, cnt, 0.f);
+                    }
+                    wait_buf((g0 + (uint32_t)spb) & 1u);
+                    if (valid > FSUB * spb + 16 * wg) {
+                        tmem_ld16_issue(t_lane + FSUB * spb + 16 * wg, cv);
+                        tmem_ld16_wait(cv);
+                        stats_math(cv, spb);
+                    }
+                    // ---- context norm: merge the 3 unit streams of this CTA, publish the slice's (mean, M2), signal the
+                    //      peers (remote mbarrier arrive), pull their partials over DSMEM (channel owners only: the DSMEM
+                    //      port is the bottleneck), merge.  All counts are constants of the launch: no divisions.
+                    {
+                        const float m = K + s1 * inv_cnt_wg;
+                        const float M2 = fmaxf(fmaf(-s1 * inv_cnt_wg, s1, s2), 0.f);
+                        part2_s[wg * CH + ch] = make_float2(m, M2);
                     }
                     conv_sync();
                     if (wg == 0) {
-                        float m = 0.f, M2 = 0.f, c = 0.f;
+                        {
+                            float2 p[3];
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const float4 p = part_s[q * CH + ch];
-                            if (p.z > 0.f) chan_merge(m, M2, c, p.x, p.y, p.z);
+                            for (int q = 0; q < 3; ++q) p[q] = part2_s[q * CH + ch];
+                            float m = 0.f, M2 = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) m = fmaf(tab_s[q].y, p[q].x, m);
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float d = p[q].x - m;
+                                M2 += fmaf(tab_s[q].x * d, d, p[q].y);
+                            }
+                            own_s[xpar * CH + ch] = make_float2(m, M2);
                         }
-                        own_s[xpar * CH + ch] = make_float2(m, M2);
-                    }
-                    cluster_arrive();
-                    cluster_wait();
-                    float m = 0.f, M2 = 0.f, c = 0.f;
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (tid < FCS) mbar_arrive_remote(bar + BAR_XCHG, (uint32_t)tid);
+                        mbar_wait_cluster(bar + BAR_XCHG, xpar);
+                        float2 p[FCS];
 #pragma unroll
-                    for (int r = 0; r < FCS; ++r) {
-                        const float2 p = ld_cluster_f2(own_s + xpar * CH + ch, (uint32_t)r);
-                        const float pc = (float)max(0, min(ES, E - r * ES));
-                        if (pc > 0.f) chan_merge(m, M2, c, p.x, p.y, pc);
+                        for (int r = 0; r < FCS; ++r) p[r] = ld_cluster_f2(own_s + xpar * CH + ch, (uint32_t)r);
+                        float m = 0.f, M2 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < FCS; ++r) m = fmaf(tab_s[4 + r].y, p[r].x, m);
+#pragma unroll
+                        for (int r = 0; r < FCS; ++r) {
+                            const float d = p[r].x - m;
+                            M2 += fmaf(tab_s[4 + r].x * d, d, p[r].y);
+                        }
+                        const float var = M2 * inv_em1;
+                        stat_s[ch] = make_float2(m, 1.0f / sqrtf(var + 1e-3f));
                     }
-                    const float var = M2 / (float)(E - 1);
-                    st = make_float2(m, 1.0f / sqrtf(var + 1e-3f));
+                    conv_sync();
+                    st = stat_s[ch];
                     xpar ^= 1u;
                 }
                 un_in = un_out;
