@@ -20,6 +20,25 @@
 #include "gmw_tc_common.cuh"
 
 namespace dcd {
+// Optional in-kernel timeline (build with -DDCD_FUSED_TRACE, see profiles/trace_fused.py): lane 0 of converter warp 0
+// and of the MMA warp of CTA 0 record (tag, clock64) pairs; read back with dcd_debug_fused_trace().
+#ifdef DCD_FUSED_TRACE
+__device__ long long g_trace[8192];
+__device__ int g_trace_n[2];
+#define TR_DECL const bool trace_on = blockIdx.x == 0 && (warp == 0 || warp == FCONV_WARPS); int tr_k = 0;
+#define TR(slot, tag)                                                       \
+    do {                                                                    \
+        if (trace_on && lane == 0 && tr_k < 2048) {                         \
+            g_trace[(slot) * 4096 + 2 * tr_k] = (tag);                      \
+            g_trace[(slot) * 4096 + 2 * tr_k + 1] = clock64();              \
+            ++tr_k;                                                         \
+            g_trace_n[slot] = tr_k;                                         \
+        }                                                                   \
+    } while (0)
+#else
+#define TR_DECL
+#define TR(slot, tag) do { } while (0)
+#endif
 namespace {
 
 constexpr int FCS = 8;              // CTAs per cluster = edge slices per object
@@ -224,6 +243,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+    TR_DECL
     const int ch = 32 * quarter + lane;                      // this thread's channel = TMEM lane = weight row
     const uint32_t rank = cluster_ctarank();
     const int E = L.E, EP = L.EP, depth = L.depth;
@@ -315,13 +335,17 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
             const int mat_base = (int)(item & 1) * nphase;
             for (int ph = 0; ph < nphase; ++ph) {
                 if (warp == FCONV_WARPS) {
+                    TR(1, 10);
                     mbar_wait(bar + BAR_WREADY, wpar);
                     tc_fence_after();
+                    TR(1, 11);
                     for (int s = 0; s < nsub; ++s, ++g) {
                         const uint32_t b = g & 1u;
+                        TR(1, 100 + s);
                         mbar_wait(bar + BAR_FULL0 + b, (fpar >> b) & 1u);
                         fpar ^= 1u << b;
                         tc_fence_after();
+                        TR(1, 200 + s);
                         if (elect_one()) {
                             const uint32_t b_hi = smem_u32(Bbuf) + b * 2 * FB_PART;
                             issue_sub_gemm(tmem_base + FSUB * s, tmem_base + FT_W, tmem_base + FT_W + 64, b_hi, b_hi + FB_PART,
@@ -339,12 +363,15 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                 if (more) {
                     const uint4* src = w_src(last_ph ? (int)((item + item_step) & 1) * nphase : mat_base + ph + 1);
                     w_load(src, 0);
+                    TR(1, 20);
                     mbar_wait(bar + BAR_PDONE, ppar);
                     tc_fence_after();
+                    TR(1, 21);
                     w_store(0);
                     w_load(src, 1);
                     w_store(1);
                     w_publish();
+                    TR(1, 22);
                 } else {
                     mbar_wait(bar + BAR_PDONE, ppar);
                 }
@@ -502,7 +529,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                 if (reads_d && unit0) tmem_ld16_issue(t_lane + 16 * wg, cv);
                 for (int s = 0; s < nsub; ++s, ++g) {
                     const uint32_t b = g & 1u;
+                    TR(0, 1000 * kind + 100 + s);
                     wait_buf(b);
+                    TR(0, 1000 * kind + 200 + s);
                     unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
                     const int col0 = FSUB * s + 16 * wg;
                     const bool active = col0 < ES;
@@ -515,6 +544,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
                     }
                     if (reads_d && active) tmem_ld16_wait(cv);
+                    TR(0, 1000 * kind + 300 + s);
                     if (do_stats) tmem_ld16_issue(t_lane + col0 - 2 * FSUB, sv);
                     if (active) {
                         if (kind == 0) {
@@ -551,15 +581,18 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         }
                         store_unit(b_hi, b_hi + FB_PART, ch, wg, v);
                     }
+                    TR(0, 1000 * kind + 400 + s);
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + BAR_FULL0 + b);
                     pend |= 1u << b;
+                    TR(0, 1000 * kind + 500 + s);
                     if (do_stats) tmem_ld16_wait(sv);
                     if (reads_d && s + 1 < nsub && col0 + FSUB < ES) tmem_ld16_issue(t_lane + col0 + FSUB, cv);
                     if (do_stats) stats_math(sv, s - 2);
                 }
+                TR(0, 1000 * kind + 600);
                 if (stats) {
                     // the last two sub-tiles' statistics: the first overlaps the drain of the last MMAs
                     const int spa = nsub - 2, spb = nsub - 1;
@@ -571,7 +604,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                             stats_math(sv, spa);
                         }
                     }
+                    TR(0, 1000 * kind + 601);
                     wait_buf((g0 + (uint32_t)spb) & 1u);
+                    TR(0, 1000 * kind + 602);
                     if (valid > FSUB * spb + 16 * wg) {
                         tmem_ld16_issue(t_lane + FSUB * spb + 16 * wg, cv);
                         tmem_ld16_wait(cv);
@@ -585,7 +620,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         const float M2 = fmaxf(fmaf(-s1 * inv_cnt_wg, s1, s2), 0.f);
                         part2_s[wg * CH + ch] = make_float2(m, M2);
                     }
+                    TR(0, 1000 * kind + 603);
                     conv_sync();
+                    TR(0, 1000 * kind + 604);
                     if (wg == 0) {
                         {
                             float2 p[3];
@@ -603,7 +640,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         }
                         asm volatile("bar.sync 2, 128;" ::: "memory");
                         if (tid < FCS) mbar_arrive_remote(bar + BAR_XCHG, (uint32_t)tid);
+                        TR(0, 1000 * kind + 605);
                         mbar_wait_cluster(bar + BAR_XCHG, xpar);
+                        TR(0, 1000 * kind + 606);
                         float2 p[FCS];
 #pragma unroll
                         for (int r = 0; r < FCS; ++r) p[r] = ld_cluster_f2(own_s + xpar * CH + ch, (uint32_t)r);
@@ -617,8 +656,10 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         }
                         const float var = M2 * inv_em1;
                         stat_s[ch] = make_float2(m, 1.0f / sqrtf(var + 1e-3f));
+                        TR(0, 1000 * kind + 607);
                     }
                     conv_sync();
+                    TR(0, 1000 * kind + 608);
                     st = stat_s[ch];
                     xpar ^= 1u;
                 }
@@ -666,6 +707,17 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
 }
 
 }  // namespace
+
+#ifdef DCD_FUSED_TRACE
+}  // namespace dcd
+extern "C" __attribute__((visibility("default"))) int dcd_debug_fused_trace(long long* dst, int* n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, dcd::g_trace, sizeof(long long) * 8192);
+    cudaMemcpyFromSymbol(n, dcd::g_trace_n, sizeof(int) * 2);
+    return 0;
+}
+namespace dcd {
+#endif
 
 bool gmw_fused_supported(int n) {
     const int E = n * (n - 1) / 2;

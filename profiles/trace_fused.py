@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""In-kernel timeline of the fused GMW forward (debug aid, not a benchmark).
+
+Build the library with the trace hooks, run this on a GPU, then rebuild without them:
+
+    DCD_B200_NVCC_EXTRA=-DDCD_FUSED_TRACE python -m dcd_b200.build --force
+    gpurun -- 'python profiles/trace_fused.py > gpurun_out/trace.txt'
+    python -m dcd_b200.build --force
+
+Prints "slot tag delta_cycles" (slot 0 = converter warp 0, slot 1 = MMA warp of CTA 0).  Converter tags:
+1000*kind + {100 step start, 200 operand buffer free, 300 accumulators loaded, 400 operand stored, 500 arrived}
++ sub-tile, 600.. = end-of-layer statistics and exchange; MMA warp: 100+s wait for operand, 200+s operand ready,
+10/11 weights ready, 20/21/22 next weights: prefetched / layer's MMAs complete / published.
+"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dcd_b200  # noqa: E402
+from dcd_b200 import _lib, synth  # noqa: E402
+
+ob = synth.make_objects(N=8, n=73, seed=5)
+model = dcd_b200.GMW(depth=12).cuda().load_reference_state_dict(synth.random_state_dict(7))
+with torch.no_grad():
+    model(ob.kps_norm.cuda(), ob.kps_3d.cuda())
+torch.cuda.synchronize()
+L = ctypes.CDLL(_lib.LIB_PATH)
+buf = (ctypes.c_longlong * 8192)()
+n = (ctypes.c_int * 2)()
+L.dcd_debug_fused_trace(buf, n)
+for slot in range(2):
+    prev = None
+    for i in range(min(n[slot], 2048)):
+        tag, t = buf[slot * 4096 + 2 * i], buf[slot * 4096 + 2 * i + 1]
+        print(slot, tag, t - (prev if prev is not None else t))
+        prev = t
