@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
     const int net = blockIdx.y;
     const int cin = net == 0 ? 4 : 6;
     const float* __restrict__ prm = a.params[net];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (MMA issue on the uniform datapath)
     const int quarter = warp & 3, cq = warp >> 2;           // TMEM lane quarter / column quarter (32 edges) in epilogues
     const int E = L.E, EP = L.EP, T = L.T;
 
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const int ch = 32 * quarter + lane;
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
     const float2 wsc = __ldg(a.scales + mat);
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             // weight gradient: D_w[o][i] += sum_e A1[o][e] A2[i][e]   (both K-major views, accumulates over tiles)
             uint32_t acc = (t == t_begin) ? 0u : 1u;

@@ -90,11 +90,6 @@ __device__ __forceinline__ float2 ld_cluster_f2(const void* local, uint32_t rank
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void conv_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FCONV_THREADS) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {

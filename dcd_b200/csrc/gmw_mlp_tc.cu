@@ -73,7 +73,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const int net = blockIdx.y;
     const int cin = net == 0 ? 4 : 6;
     const float* __restrict__ prm = a.params[net];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (MMA issue on the uniform datapath)
     const int group = warp >> 3, gwarp = warp & 7, gtid = tid & (GROUP_THREADS - 1);
     const int quarter = gwarp & 3, hsel = gwarp >> 2;      // TMEM lane quarter / column half owned in the epilogues
     const int E = L.E, EP = L.EP, T = L.T;
@@ -99,7 +100,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const int ch = 32 * quarter + lane;                     // this thread's TMEM lane = output channel
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
     const float2 sc0 = __ldg(scales + mat0);
@@ -269,10 +270,13 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
         tc_fence_before();
         group_sync(group);
         // ---- GEMM 1
-        if (gtid == 0) {
-            tc_fence_after();
-            issue_layer_gemm(tmem_d, tmem_base + TM_W0_HI, tmem_base + TM_W0_LO, smem_u32(B_hi), smem_u32(B_lo));
-            umma_commit(bar_mma);
+        if (gwarp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+                issue_layer_gemm(tmem_d, tmem_base + TM_W0_HI, tmem_base + TM_W0_LO, smem_u32(B_hi), smem_u32(B_lo));
+                umma_commit(bar_mma);
+            }
+            __syncwarp();
         }
         if (t + 1 < t_end) prefetch(t + 1);
         mbar_wait(bar_mma, mma_phase);
@@ -304,10 +308,13 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
             tc_fence_before();
             group_sync(group);
             // ---- GEMM 2 (conv1)
-            if (gtid == 0) {
-                tc_fence_after();
-                issue_layer_gemm(tmem_d, tmem_base + TM_W1_HI, tmem_base + TM_W1_LO, smem_u32(B_hi), smem_u32(B_lo));
-                umma_commit(bar_mma);
+            if (gwarp == 0) {
+                if (elect_one()) {
+                    tc_fence_after();
+                    issue_layer_gemm(tmem_d, tmem_base + TM_W1_HI, tmem_base + TM_W1_LO, smem_u32(B_hi), smem_u32(B_lo));
+                    umma_commit(bar_mma);
+                }
+                __syncwarp();
             }
             mbar_wait(bar_mma, mma_phase);
             mma_phase ^= 1;

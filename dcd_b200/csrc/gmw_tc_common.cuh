@@ -28,6 +28,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// One lane of a converged warp.  Issuing tcgen05.mma under this predicate (with warp-uniform operands: derive
+// warp indices and tensor-memory addresses through __shfl_sync(.., 0)) lets the compiler keep descriptors in
+// uniform registers; under `if (threadIdx.x == 0)` it emits a 14-instruction R2UR "waterfall" per MMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
