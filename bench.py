@@ -40,6 +40,7 @@ WEIGHT_SEED = 7
 F_SOLVE = 6 * N_KPTS + 11 * EDGES                 # 29 346 FLOP
 B_SOLVE = 20 * N_KPTS + 56                        # 1516 B in + mean out
 F_MLP = EDGES * (2 * 128 * (4 + 6) + 36 * 2 * 2 * 128 * 128)     # 6.207 GFLOP (both nets, GEMM FLOPs only)
+FUSED_TRAFFIC_2048 = 5.61e9      # ncu: dram read 15 MB + write 5.59 GB for one fused launch on 2048 objects
 
 
 def parse():
@@ -251,7 +252,8 @@ def main():
                 mlp_events.append((e0, e1, nc))
             check(L.dcd_gmw_aggregate_fwd(ptr(regw), ptr(zsel), ptr(idx), nc, EDGES, K_SEL, 1, ptr(depth_out[c0:]), 0, st),
                   "aggregate")
-            launches[0] += 1 + (1 + DEPTH + (DEPTH - 1) + 1) + 1
+            # select | weight scales, weight image, fused MLP (all layers of both nets), edge weights | aggregate
+            launches[0] += 1 + 4 + 1
 
     def gather():
         if world > 1:
@@ -362,7 +364,8 @@ def main():
         value = N_total * args.steps / (ms * 1e-3)
         e2e_value = N_total * args.steps / (e2e_ms * 1e-3)
         mlp_tflops = F_MLP * mlp_objs / (mlp_ms * 1e-3) / 1e12
-        n_mlp_launches = len(mlp_events) * (1 + DEPTH + DEPTH - 1)
+        n_mlp_launches = len(mlp_events)
+        out_bytes = 2 * 128 * 128 * ((EDGES + 127) // 128) * 4            # final features of both nets, per object
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -371,24 +374,29 @@ def main():
                                    "(%d objects per GPU), 73 keypoints, 2628 edges: compute_z + edge-weight MLP + "
                                    "softmax-weighted depth, forward only%s" % (args.frames, N, ", + all-gather of depths" if world > 1 else ""),
                        "objects_per_gpu": N, "objects_total": N_total, "chunk_objects": chunk, "net_depth": DEPTH,
-                       "l2_policy": "inputs and MLP workspace (%.1f GB) larger than L2" % (ws.numel() * 4 / 1e9),
+                       "l2_policy": "every chunk streams %.1f GB of final features through L2 (126 MB): nothing survives between "
+                                    "chunks or steps" % (min(chunk, N) * 2 * 128 * 128 * ((EDGES + 127) // 128) * 4 / 1e9),
                        "weights": "random init, seed %d, reference state_dict layout" % WEIGHT_SEED},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": N * 4,
                     "api": "dcd_b200.gmw_weighted_depth on pinned host tensors"},
             "gpu_launches": timed_launches,
-            "roofline": {"kernel": "mlp_tc_kernel<FIRST|B|CA> (edge-feature MLP: 36 GEMM layers x 2 nets on tcgen05, FP16x3 split, "
-                                   "FP32 accumulate in TMEM)", "bound": "tensor",
+            "roofline": {"kernel": "mlp_fused_kernel (edge-feature MLP, all 37 layers of a net in one cluster-of-8 launch: activations "
+                                   "stay in shared/tensor memory, 36 GEMM layers x 2 nets on tcgen05, FP16x3 split, FP32 accumulate in TMEM)",
+                         "bound": "tensor",
                          "achieved": mlp_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": mlp_tflops / peaks["bf16_tflops_sustained"],
-                         # ncu dram__bytes_read+write of ONE mlp_tc_kernel<CA> launch on a 2048-object chunk
-                         # (profiles/r01_mlp_tc_kernel.md); the layer-wise schedule's model for that launch is 2048 x 11.0 MB
-                         "traffic": 22.93e9 if chunk == 2048 else None,
+                         # ncu dram__bytes_read+write of ONE mlp_fused_kernel launch on a 2048-object chunk
+                         # (profiles/r01_mlp_fused_kernel.md); algorithmic: 2048 x 2.75 MB of final features out
+                         "traffic": FUSED_TRAFFIC_2048 if chunk == 2048 else None,
                          "peak_source": "%s dense bf16 (sustained, of measured); `achieved` counts the algorithmic FP32 GEMM FLOPs, the "
                                         "tensor pipe executes 3 FP16 MMAs per FP32 product (x3 = %.1f TFLOP/s issued); vs the FP32 "
-                                        "CUDA-core roofline (%.1f TFLOP/s) the same number is %.2fx" % (
+                                        "CUDA-core roofline (%.1f TFLOP/s) the same number is %.2fx. The events bracket dcd_gmw_weights_fwd "
+                                        "(weight scales + weight image + fused MLP + edge weights; the fused kernel is ~97%% of it)" % (
                                             peaks["source"], 3 * mlp_tflops, fp32_peak, mlp_tflops / fp32_peak),
-                         "hbm_gbs": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9, "frac_hbm": 198.0e6 * mlp_objs / (mlp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "hbm_bytes_per_object": 198.0e6, "frac_fp32_roofline": mlp_tflops / fp32_peak,
+                         "hbm_gbs": out_bytes * mlp_objs / (mlp_ms * 1e-3) / 1e9,
+                         "frac_hbm": out_bytes * mlp_objs / (mlp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "hbm_bytes_per_object": out_bytes, "hbm_bytes_per_object_layerwise": 198.0e6,
+                         "frac_fp32_roofline": mlp_tflops / fp32_peak,
                          "flops_per_object": F_MLP, "avg_launch_ms": mlp_ms / max(n_mlp_launches, 1),
                          "share_of_step": mlp_ms_max / ms},
             "stages": {

@@ -87,6 +87,12 @@ __device__ __forceinline__ float2 ld_cluster_f2(const void* local, uint32_t rank
     asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
     return v;
 }
+// weight image: read-only, re-read by every CTA for every layer -> keep it in L2 against the streamed outputs
+__device__ __forceinline__ void ld_weights8(const uint32_t* p, uint32_t* r) {
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -293,13 +299,10 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
         // service warps: stream the layers' weight images into tensor memory; the first one issues the MMAs
         // =====================================================================================================
         uint32_t wr[64];
-        auto w_src = [&](int mat) { return reinterpret_cast<const uint4*>(wimg + ((size_t)mat * CH + ch) * CH); };
-        auto w_load = [&](const uint4* src, int half) {
+        auto w_src = [&](int mat) { return wimg + ((size_t)mat * CH + ch) * CH; };
+        auto w_load = [&](const uint32_t* src, int half) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint4 v = __ldg(src + 16 * half + i);
-                wr[4 * i] = v.x; wr[4 * i + 1] = v.y; wr[4 * i + 2] = v.z; wr[4 * i + 3] = v.w;
-            }
+            for (int i = 0; i < 8; ++i) ld_weights8(src + 64 * half + 8 * i, wr + 8 * i);
         };
         auto w_store = [&](int half) {
             uint32_t t[32];
@@ -319,7 +322,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
         uint32_t g = 0;                                       // running sub-tile step: operand buffer = g & 1
         uint32_t fpar = 0, wpar = 0, ppar = 0;                // parities: full[2] (bits), wready, pdone
         if (item0 < nitems) {
-            const uint4* src = w_src((int)(item0 & 1) * nphase);
+            const uint32_t* src = w_src((int)(item0 & 1) * nphase);
             w_load(src, 0);
             w_store(0);
             w_load(src, 1);
@@ -356,7 +359,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                 const bool last_ph = ph + 1 == nphase;
                 const bool more = !last_ph || item + item_step < nitems;
                 if (more) {
-                    const uint4* src = w_src(last_ph ? (int)((item + item_step) & 1) * nphase : mat_base + ph + 1);
+                    const uint32_t* src = w_src(last_ph ? (int)((item + item_step) & 1) * nphase : mat_base + ph + 1);
                     w_load(src, 0);
                     TR(1, 20);
                     mbar_wait(bar + BAR_PDONE, ppar);
@@ -686,7 +689,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
-                        *reinterpret_cast<float4*>(G + col0 + 4 * q4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        __stcs(reinterpret_cast<float4*>(G + col0 + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));   // streamed: keep the weight image in L2
                 }
                 tc_fence_before();                            // the next item's MMAs overwrite these columns
             }

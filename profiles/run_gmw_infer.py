@@ -13,7 +13,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dcd_b200  # noqa: E402
-from dcd_b200 import synth  # noqa: E402
+from dcd_b200 import _lib, synth  # noqa: E402
+
+if os.environ.get("DCD_B200_LIB"):            # experiment builds of the library
+    _lib._lib = _lib.load_library(os.environ["DCD_B200_LIB"])
 
 
 def main():
