@@ -1,12 +1,14 @@
 // GMW edge-feature MLP forward, inference form: ONE kernel for all 37 layers of a net, the object's
-// activations never leave the chip (sm_100a: thread-block clusters + tcgen05 + TMEM).
+// activations never leave the chip (sm_100a: tcgen05 + TMEM, persistent co-resident CTA groups).
 //
 // The layer-wise kernels (gmw_mlp_tc.cu) are bound by HBM: every context norm needs the statistics of the
 // whole object, so each of the 24 normalised layers writes its output and reads it back (198 MB / object).
-// Here a cluster of 8 CTAs owns one (object, net): CTA r holds the edge slice [r*ES, (r+1)*ES) of ALL 128
+// Here a group of 8 CTAs owns one (object, net): CTA r holds the edge slice [r*ES, (r+1)*ES) of ALL 128
 // channels on chip for the whole network, and the only thing the CTAs exchange per context norm is the
-// per-channel (mean, M2) partial of their slice, read from each other's shared memory (DSMEM) after a
-// cluster barrier.  Per CTA (ES <= 336 edges, E <= 2688, i.e. up to the reference's n = 73 keypoints):
+// per-channel (mean, M2) partial of their slice (1 KB per CTA, through L2 with self-validating words: no
+// fences, no barriers).  Groups are plain consecutive CTAs of a cooperative launch (all CTAs resident, one per
+// SM): 18 groups use 144 of the 148 SMs, where hardware clusters of 8 can only be placed on 120.
+// Per CTA (ES <= 336 edges, E <= 2688, i.e. up to the reference's n = 73 keypoints):
 //   * residual stream X        : FP32 in shared memory, [ES/4][128 ch] float4            (172 KB)
 //   * layer output (P, Y1, Y2) : FP32 accumulators in tensor memory, columns [0, ES)     (336 of 512 columns);
 //                                every GEMM overwrites its own input sub-tile in place
@@ -14,9 +16,12 @@
 //                                reloaded per layer from an L2-resident pre-split image (64 KB / layer)
 //   * B operand                : two 24 KB buffers (hi + lo of a 48-edge sub-tile, MN-major, no swizzle),
 //                                written by the threads that produce the values (thread = channel)
-// Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, Chan-merged
-// statistics); only the order in which the statistics partials are merged differs.
-// HBM traffic: keypoints in, final features out (2.7 MB / object instead of 198 MB).
+// Warp roles: 12 converter warps (thread = channel; accumulators -> context norm / ReLU / residual -> FP16
+// hi/lo operand; statistics of the layer output), 4 service warps (weight image -> tensor memory; the first one
+// issues the MMAs from an elected lane).  Hand-offs are mbarriers; there is no CTA-wide barrier per sub-tile.
+// Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, FP32 statistics);
+// only the order in which the statistics partials are merged differs.
+// HBM traffic: keypoints in, final features out (2.75 MB / object instead of 198 MB).
 #include "gmw_tc_common.cuh"
 
 namespace dcd {
@@ -55,36 +60,23 @@ constexpr uint32_t FB_PART = 16 * FB_LBO;   // 12 KB: hi or lo part of one sub-t
 constexpr size_t SMF_X = 0;
 constexpr size_t SMF_B = SMF_X + (size_t)FES_MAX * CH * sizeof(float);          // [2 buffers]{hi, lo}
 constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [3][128] float2 (mean, M2) + count tables
-constexpr size_t SMF_OWN = SMF_PART + 3 * CH * sizeof(float4);                  // [2 parities][128] float2
-constexpr size_t SMF_BAR = SMF_OWN + 2 * CH * sizeof(float2);
+constexpr size_t SMF_BAR = SMF_PART + 3 * CH * sizeof(float4);
 constexpr size_t kFusedSmem = SMF_BAR + 128;
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 static_assert(6 * FES_MAX * sizeof(float) <= 4 * FB_PART, "edge features are staged in the operand buffers");
 // mbarriers (8 bytes each, at SMF_BAR)
-enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_XCHG = 6, BAR_COUNT = 7 };
+enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_COUNT = 6 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
+// Statistics exchange between the 8 CTAs of a group through global memory (L2): every published 8-byte word carries
+// its own "ready" flag in the sign bit of its second float (an M2 is never negative), so there are no fences, no
+// barriers and no ordering requirements: a reader re-reads a word until the flag matches the expected use count.
+__device__ __forceinline__ void st_flagged(float2* dst, float a, float b, uint32_t flag) {
+    const uint32_t bits = (__float_as_uint(b) & 0x7fffffffu) | (flag << 31);
+    asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(__uint_as_float(bits)) : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_id_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_count_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float2 ld_cluster_f2(const void* local, uint32_t rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+__device__ __forceinline__ float2 ld_volatile_f2(const float2* p) {
     float2 v;
-    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
 // weight image: read-only, re-read by every CTA for every layer -> keep it in L2 against the streamed outputs
@@ -145,24 +137,6 @@ __device__ __forceinline__ void fadd2_acc(float& s0, float& s1, float d0, float 
     asm("{\n\t.reg .b64 d, s;\n\tmov.b64 d, {%2, %3};\n\tmov.b64 s, {%0, %1};\n\t"
         "add.rn.f32x2 s, s, d;\n\tmov.b64 {%0, %1}, s;\n\t}"
         : "+f"(s0), "+f"(s1) : "f"(d0), "f"(d1));
-}
-
-// cluster-scope mbarrier signalling: arrive on the barrier of CTA `rank`, wait on the local one
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "XWAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra XWAIT_DONE;\n\t"
-        "bra XWAIT_LOOP;\n\t"
-        "XWAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // no-swizzle (interleaved) shared-memory matrix descriptor
@@ -238,15 +212,15 @@ __global__ void __launch_bounds__(256) tc_weight_image_kernel(const float* __res
 
 namespace {
 
-__global__ void __cluster_dims__(FCS, 1, 1) __launch_bounds__(FTHREADS, 1)
-mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* __restrict__ wimg) {
+__global__ void __launch_bounds__(FTHREADS, 1)
+mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* __restrict__ wimg, float2* xg) {
     const WsLayout& L = a.L;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
     TR_DECL
     const int ch = 32 * quarter + lane;                      // this thread's channel = TMEM lane = weight row
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = blockIdx.x % FCS, group = blockIdx.x / FCS;   // 8 consecutive CTAs form a group (co-resident: cooperative launch)
     const int E = L.E, EP = L.EP, depth = L.depth;
     const int ES = 16 * ((E + 127) / 128);                   // edges per CTA (8 * ES == EP)
     const int nsub = (ES + FSUB - 1) / FSUB;
@@ -258,7 +232,6 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
     float2* part2_s = reinterpret_cast<float2*>(smem + SMF_PART);            // [3][128] (mean, M2) per unit stream
     float2* tab_s = reinterpret_cast<float2*>(smem + SMF_PART + 3 * CH * sizeof(float2));   // counts, see below
     float2* stat_s = tab_s + 16;                                                    // [128] (mean, rstd) of the current context norm
-    float2* own_s = reinterpret_cast<float2*>(smem + SMF_OWN);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMF_BAR);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMF_BAR + 8 * BAR_COUNT);
 
@@ -269,7 +242,6 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
         mbar_init(bar + BAR_DONE1, 1);
         mbar_init(bar + BAR_PDONE, 1);
         mbar_init(bar + BAR_WREADY, 4);
-        mbar_init(bar + BAR_XCHG, FCS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // statistics merge weights: tab_s[q] = (n_q, n_q / n_cta) for the 3 unit streams of this CTA (q = 0..2),
@@ -287,12 +259,10 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    cluster_arrive();                                       // peers' mbarriers are initialised before any remote arrive
-    cluster_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const int64_t nitems = L.N * 2;
-    const int64_t item0 = cluster_id_x(), item_step = cluster_count_x();
+    const int64_t item0 = group, item_step = gridDim.x / FCS;
 
     if (warp >= FCONV_WARPS) {
         // =====================================================================================================
@@ -393,7 +363,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                 tc_fence_after();
             }
         };
-        uint32_t xpar = 0;                                    // parity of the statistics exchange slot
+        uint32_t xcount = 0;                                  // statistics exchanges done: slot = count & 1, flag = (count >> 1) & 1
         const float inv_cnt_wg = tab_s[wg].x > 0.f ? 1.0f / tab_s[wg].x : 0.f;
         const float inv_em1 = 1.0f / (float)(E - 1);
 
@@ -610,9 +580,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                         tmem_ld16_wait(cv);
                         stats_math(cv, spb);
                     }
-                    // ---- context norm: merge the 3 unit streams of this CTA, publish the slice's (mean, M2), signal the
-                    //      peers (remote mbarrier arrive), pull their partials over DSMEM (channel owners only: the DSMEM
-                    //      port is the bottleneck), merge.  All counts are constants of the launch: no divisions.
+                    // ---- context norm: merge the 3 unit streams of this CTA, publish the slice's (mean, M2) in global memory,
+                    //      collect the 7 other slices of the group (flagged words, see st_flagged), merge.  The channel owners
+                    //      do this; all counts are constants of the launch: no divisions.
                     {
                         const float m = K + s1 * inv_cnt_wg;
                         const float M2 = fmaxf(fmaf(-s1 * inv_cnt_wg, s1, s2), 0.f);
@@ -622,28 +592,40 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     conv_sync();
                     TR(0, 1000 * kind + 604);
                     if (wg == 0) {
+                        const uint32_t slot = xcount & 1u, flag = (xcount >> 1) & 1u;
+                        float2* xrow = xg + ((size_t)(group * 2 + slot) * FCS) * CH + ch;      // [rank][128] of this group and slot
+                        float2 p[FCS];
                         {
-                            float2 p[3];
+                            float2 q[3];
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) p[q] = part2_s[q * CH + ch];
+                            for (int k = 0; k < 3; ++k) q[k] = part2_s[k * CH + ch];
                             float m = 0.f, M2 = 0.f;
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) m = fmaf(tab_s[q].y, p[q].x, m);
+                            for (int k = 0; k < 3; ++k) m = fmaf(tab_s[k].y, q[k].x, m);
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const float d = p[q].x - m;
-                                M2 += fmaf(tab_s[q].x * d, d, p[q].y);
+                            for (int k = 0; k < 3; ++k) {
+                                const float d = q[k].x - m;
+                                M2 += fmaf(tab_s[k].x * d, d, q[k].y);
                             }
-                            own_s[xpar * CH + ch] = make_float2(m, M2);
-                        }
-                        asm volatile("bar.sync 2, 128;" ::: "memory");
-                        if (tid < FCS) mbar_arrive_remote(bar + BAR_XCHG, (uint32_t)tid);
-                        TR(0, 1000 * kind + 605);
-                        mbar_wait_cluster(bar + BAR_XCHG, xpar);
-                        TR(0, 1000 * kind + 606);
-                        float2 p[FCS];
+                            st_flagged(xrow + rank * CH, m, M2, flag);
 #pragma unroll
-                        for (int r = 0; r < FCS; ++r) p[r] = ld_cluster_f2(own_s + xpar * CH + ch, (uint32_t)r);
+                            for (int r = 0; r < FCS; ++r) p[r] = make_float2(m, M2);            // (own slice; the others below)
+                        }
+                        TR(0, 1000 * kind + 605);
+                        uint32_t pending = ((1u << FCS) - 1u) & ~(1u << rank);
+                        while (pending) {
+                            float2 v[FCS];
+#pragma unroll
+                            for (int r = 0; r < FCS; ++r)
+                                if ((pending >> r) & 1u) v[r] = ld_volatile_f2(xrow + r * CH);
+#pragma unroll
+                            for (int r = 0; r < FCS; ++r)
+                                if (((pending >> r) & 1u) && (__float_as_uint(v[r].y) >> 31) == flag) {
+                                    p[r] = make_float2(v[r].x, __uint_as_float(__float_as_uint(v[r].y) & 0x7fffffffu));
+                                    pending &= ~(1u << r);
+                                }
+                        }
+                        TR(0, 1000 * kind + 606);
                         float m = 0.f, M2 = 0.f;
 #pragma unroll
                         for (int r = 0; r < FCS; ++r) m = fmaf(tab_s[4 + r].y, p[r].x, m);
@@ -659,7 +641,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
                     conv_sync();
                     TR(0, 1000 * kind + 608);
                     st = stat_s[ch];
-                    xpar ^= 1u;
+                    ++xcount;
                 }
                 un_in = un_out;
                 b_in = b_out;
@@ -695,10 +677,6 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
             }
         }
     }
-    // nobody may leave while a peer can still read its statistics slot
-    __syncwarp();
-    cluster_arrive();
-    cluster_wait();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -722,37 +700,43 @@ bool gmw_fused_supported(int n) {
     return 16 * ((E + 127) / 128) <= FES_MAX;
 }
 
-size_t gmw_fused_image_bytes(int depth) { return (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t); }
+constexpr int FMAX_GROUPS = 32;                               // exchange buffer sized for up to 256 SMs
+constexpr size_t kExchangeBytes = (size_t)FMAX_GROUPS * 2 * FCS * CH * sizeof(float2);
+
+// appended to the workspace: pre-split weight image, then the statistics exchange buffer [group][slot][rank][128] float2
+size_t gmw_fused_image_bytes(int depth) { return (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t) + kExchangeBytes; }
 
 // Runs both nets of all objects; the final features land in SLOT_X of the (inference-layout) workspace.
 int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, const float2* scales,
                          uint32_t* wimg, cudaStream_t st) {
     const int depth = a.L.depth;
     tc_weight_image_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales, wimg);
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    // The CTAs of a group wait for each other, so all of them must be resident: cooperative launch, one CTA per SM.
+    static int max_groups = 0;
+    if (max_groups == 0) {
         cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(FCS * 64);
-        cfg.blockDim = dim3(FTHREADS);
-        cfg.dynamicSmemBytes = kFusedSmem;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = FCS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        int nc = 0;
-        if (cudaOccupancyMaxActiveClusters(&nc, mlp_fused_kernel, &cfg) != cudaSuccess || nc <= 0) {
-            cudaGetLastError();
-            nc = device_sm_count() / FCS - 2;
-            if (nc < 1) nc = 1;
-        }
-        max_clusters = nc;
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_fused_kernel, FTHREADS, kFusedSmem);
+        if (!coop || per_sm < 1) return DCD_E_UNSUPPORTED;
+        max_groups = device_sm_count() * per_sm / FCS;
+        if (max_groups > FMAX_GROUPS) max_groups = FMAX_GROUPS;
+        if (max_groups < 1) return DCD_E_UNSUPPORTED;
     }
+    float2* xg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(wimg) + (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t));
+    cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;
-    const int nclusters = (int)(nitems < max_clusters ? nitems : max_clusters);
-    mlp_fused_kernel<<<FCS * nclusters, FTHREADS, kFusedSmem, st>>>(a, scales, wimg);
-    DCD_CHECK_LAUNCH();
+    const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);
+    MlpArgs args = a;
+    const float2* scales_arg = scales;
+    const uint32_t* wimg_arg = wimg;
+    void* kargs[] = {&args, &scales_arg, &wimg_arg, &xg};
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mlp_fused_kernel), dim3(FCS * ngroups), dim3(FTHREADS), kargs, kFusedSmem,
+                                    st) != cudaSuccess) {
+        cudaGetLastError();
+        return DCD_E_LAUNCH;
+    }
     return DCD_OK;
 }
 
