@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--impl", default="dcd_b200", choices=["dcd_b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: the KITTI val split)")
     ap.add_argument("--chunk", type=int, default=2048, help="objects per MLP workspace chunk")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="objects of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="objects of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
