@@ -712,18 +712,22 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
     const int depth = a.L.depth;
     tc_weight_image_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales, wimg);
     // The CTAs of a group wait for each other, so all of them must be resident: cooperative launch, one CTA per SM.
-    static int max_groups = 0;
-    if (max_groups == 0) {
+    static int max_groups_of[64] = {0};                       // per device (function attributes are per context)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return DCD_E_DEVICE;
+    if (max_groups_of[dev] == 0) {
         cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
-        int dev = 0, coop = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_fused_kernel, FTHREADS, kFusedSmem);
         if (!coop || per_sm < 1) return DCD_E_UNSUPPORTED;
-        max_groups = device_sm_count() * per_sm / FCS;
-        if (max_groups > FMAX_GROUPS) max_groups = FMAX_GROUPS;
-        if (max_groups < 1) return DCD_E_UNSUPPORTED;
+        int g = device_sm_count() * per_sm / FCS;
+        if (g > FMAX_GROUPS) g = FMAX_GROUPS;
+        if (g < 1) return DCD_E_UNSUPPORTED;
+        max_groups_of[dev] = g;
     }
+    const int max_groups = max_groups_of[dev];
     float2* xg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(wimg) + (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t));
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;

@@ -99,7 +99,12 @@ int dcd_edge_solve_bwd(const float* kps, const float* kps3d, const float* rot, c
  *     W_in^T [Cin][128], b_in [128], then per block k<depth: Wp^T [128][128], bp [128], W1^T, b1, W2^T, b2
  * (transposed = [in][out]; dcd_b200.weights.pack_state_dict builds it from the reference state_dict).
  * kpts2d [N,n,2] normalised image coordinates, kpts3d [N,n,3].
- * save != 0 keeps the per-block activations in the workspace for dcd_gmw_weights_bwd.
+ * save != 0 keeps the per-block activations in the workspace for dcd_gmw_weights_bwd (layer-wise kernels, one
+ * launch per segment between context norms).  save == 0 and n <= 73 (E <= 2688): the whole network runs in ONE
+ * persistent kernel with the activations held on chip (groups of 8 co-resident CTAs per object; cooperative launch,
+ * so the device must not be oversubscribed by kernels that wait on this stream); larger n fall back to the
+ * layer-wise kernels.  Results of the two forms agree to FP32 rounding (the context-norm partial statistics are
+ * merged in a different order).  Environment: DCD_B200_LAYERWISE=1 forces the layer-wise kernels.
  * feat4 / feat6 (may be NULL): final un-normalised edge features, [N,128,E] channel-major.
  */
 size_t dcd_gmw_param_count(int cin, int depth);
