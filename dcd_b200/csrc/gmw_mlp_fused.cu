@@ -189,20 +189,65 @@ __device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, u
 
 }  // namespace
 
-// Pre-split weight image of one matrix: [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1)
-// of scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
-__global__ void __launch_bounds__(256) tc_weight_image_kernel(const float* __restrict__ p4, const float* __restrict__ p6,
-                                                              int depth, const float2* __restrict__ scales,
-                                                              uint32_t* __restrict__ img) {
+// Layer matrices of the fused forward.  There is no non-linearity between a block's preconv and conv1
+// (ops.py:125-131: x = preconv(x); x = conv1(x) -> context norm), so the two 128x128 layers are folded into one:
+//     Wf = W1 . Wp,   bf = W1 . bp + b1        (FP64 accumulation, rounded once to FP32)
+// which removes a third of the GEMM layers (24 instead of 36 per net; SURVEY 8d: report F_m with 24).
+// Per matrix m = (net, block, j) with j = 0: Wf, j = 1: W2 this kernel writes the power-of-two FP16 scale, the bias
+// and the pre-split weight image [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1) of
+// scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
+__global__ void __launch_bounds__(256) fused_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
+                                                         float2* __restrict__ scales2, float* __restrict__ bias2,
+                                                         uint32_t* __restrict__ img) {
+    extern __shared__ float wf_s[];                           // [in][out] FP32, 64 KB
+    __shared__ float red[8];
+    __shared__ float scale_s;
     const int m = blockIdx.x;
-    const int which = m % 3, blk = (m / 3) % depth, net = m / (3 * depth);
+    const int j = m & 1, blk = (m >> 1) % depth, net = m / (2 * depth);
     const int cin = net == 0 ? 4 : 6;
-    const float* Wt = (net == 0 ? p4 : p6) + blob_w(cin, blk, which);
-    const float scale = scales[m].x;
+    const float* prm = net == 0 ? p4 : p6;
+    const int tid = threadIdx.x;
+    if (j == 0) {
+        const float* Wp = prm + blob_w(cin, blk, 0);          // [in][mid]
+        const float* W1 = prm + blob_w(cin, blk, 1);          // [mid][out]
+        const int o = tid & 127;
+        for (int i = tid >> 7; i < CH; i += 2) {
+            double acc = 0.0;
+            for (int k = 0; k < CH; ++k) acc = fma((double)Wp[i * CH + k], (double)W1[k * CH + o], acc);
+            wf_s[i * CH + o] = (float)acc;
+        }
+        if (tid < CH) {
+            const float* bp = prm + blob_b(cin, blk, 0);
+            double acc = (double)prm[blob_b(cin, blk, 1) + tid];
+            for (int k = 0; k < CH; ++k) acc = fma((double)bp[k], (double)W1[k * CH + tid], acc);
+            bias2[m * CH + tid] = (float)acc;
+        }
+    } else {
+        const float* W2 = prm + blob_w(cin, blk, 2);
+        for (int i = tid; i < CH * CH; i += 256) wf_s[i] = W2[i];
+        if (tid < CH) bias2[m * CH + tid] = prm[blob_b(cin, blk, 2) + tid];
+    }
+    __syncthreads();
+    // per-matrix power-of-two scale that puts max|W| in [512, 1024): FP16 hi/lo both stay normal
+    float mx = 0.f;
+    for (int i = tid; i < CH * CH; i += 256) mx = fmaxf(mx, fabsf(wf_s[i]));
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        mx = 0.f;
+        for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        int e = 0;
+        if (mx > 0.f) frexpf(mx, &e);
+        scales2[m] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
+        scale_s = ldexpf(1.f, 10 - e);
+    }
+    __syncthreads();
+    const float scale = scale_s;
     uint32_t* out = img + (size_t)m * CH * CH;
-    for (int idx = threadIdx.x; idx < CH * 64; idx += 256) {
+    for (int idx = tid; idx < CH * 64; idx += 256) {
         const int row = idx & 127, c = idx >> 7;
-        const float w0 = Wt[(2 * c) * CH + row] * scale, w1 = Wt[(2 * c + 1) * CH + row] * scale;
+        const float w0 = wf_s[(2 * c) * CH + row] * scale, w1 = wf_s[(2 * c + 1) * CH + row] * scale;
         const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
         const __half l0 = __float2half_rn(w0 - __half2float(h0)), l1 = __float2half_rn(w1 - __half2float(h1));
         out[row * CH + c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
@@ -213,7 +258,8 @@ __global__ void __launch_bounds__(256) tc_weight_image_kernel(const float* __res
 namespace {
 
 __global__ void __launch_bounds__(FTHREADS, 1)
-mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* __restrict__ wimg, float2* xg) {
+mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __restrict__ bias2, const uint32_t* __restrict__ wimg,
+                 float2* xg) {
     const WsLayout& L = a.L;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
@@ -224,7 +270,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
     const int E = L.E, EP = L.EP, depth = L.depth;
     const int ES = 16 * ((E + 127) / 128);                   // edges per CTA (8 * ES == EP)
     const int nsub = (ES + FSUB - 1) / FSUB;
-    const int nphase = 3 * depth;
+    const int nphase = 2 * depth;                            // per block: folded preconv.conv1, conv2
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* Xs = reinterpret_cast<float4*>(smem + SMF_X);
@@ -425,19 +471,19 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const uint32_t* _
             float un_in = 0.f, b_in = 0.f;                    // scale/bias of the matrix that produced the current D
             float2 st = make_float2(0.f, 1.f);                // (mean, rstd) of the current D's context norm
             for (int ph = 0; ph < nphase; ++ph) {
-                const int blk = ph / 3, kind = ph - 3 * blk;  // 0 preconv, 1 conv1, 2 conv2
+                const int kind = (ph & 1) ? 2 : 0;            // 0: (residual update ->) folded preconv.conv1, 2: conv2
                 const float un_out = __ldg(scales + mat_base + ph).y;
-                const float b_out = __ldg(prm + blob_b(cin, blk, kind) + ch);
-                // input transform of this layer as one FMA on the raw accumulator: kind 1: + bias;
-                // kinds 0, 2: context norm of the producing layer folded in ((d*un + b - mean) * rstd)
-                const float a_in = (kind == 1) ? un_in : un_in * st.y;
-                const float c_in = (kind == 1) ? b_in : (b_in - st.x) * st.y;
+                const float b_out = __ldg(bias2 + (mat_base + ph) * CH + ch);
+                // input transform of this layer as one FMA on the raw accumulator: the context norm of the producing
+                // layer folded in ((d*un + b - mean) * rstd)
+                const float a_in = un_in * st.y;
+                const float c_in = (b_in - st.x) * st.y;
                 // statistics of this layer's output as shifted sums around K (K = mean of this thread's first unit)
                 float K = 0.f, s1 = 0.f, s2 = 0.f, bK = b_out;
                 bool have_K = false;
                 const uint32_t g0 = g;
                 const bool reads_d = ph > 0;
-                const bool stats = kind != 0;
+                const bool stats = true;                      // every GEMM layer of the folded net is normalised
 
                 // statistics of one unit from its raw accumulators
                 auto stats_math = [&](const uint32_t (&raw)[16], int sp) {
@@ -703,14 +749,24 @@ bool gmw_fused_supported(int n) {
 constexpr int FMAX_GROUPS = 32;                               // exchange buffer sized for up to 256 SMs
 constexpr size_t kExchangeBytes = (size_t)FMAX_GROUPS * 2 * FCS * CH * sizeof(float2);
 
-// appended to the workspace: pre-split weight image, then the statistics exchange buffer [group][slot][rank][128] float2
-size_t gmw_fused_image_bytes(int depth) { return (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t) + kExchangeBytes; }
+// Tail of the workspace used by the fused forward, per matrix m = (net, block, {folded preconv.conv1, conv2}):
+//   scales2 [4*depth] float2 (256-byte padded) | bias2 [4*depth][128] | weight image [4*depth][128][128] u32 | exchange buffer
+static size_t fused_scales_bytes(int depth) { return (((size_t)4 * depth * sizeof(float2)) + 255) / 256 * 256; }
+static size_t fused_bias_bytes(int depth) { return (size_t)4 * depth * CH * sizeof(float); }
+static size_t fused_image_only_bytes(int depth) { return (size_t)4 * depth * CH * CH * sizeof(uint32_t); }
+size_t gmw_fused_image_bytes(int depth) {
+    return fused_scales_bytes(depth) + fused_bias_bytes(depth) + fused_image_only_bytes(depth) + kExchangeBytes;
+}
 
 // Runs both nets of all objects; the final features land in SLOT_X of the (inference-layout) workspace.
-int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, const float2* scales,
-                         uint32_t* wimg, cudaStream_t st) {
+// `tail` points to gmw_fused_image_bytes(depth) bytes (256-byte aligned).
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st) {
     const int depth = a.L.depth;
-    tc_weight_image_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales, wimg);
+    unsigned char* base = reinterpret_cast<unsigned char*>(tail);
+    float2* scales2 = reinterpret_cast<float2*>(base);
+    float* bias2 = reinterpret_cast<float*>(base + fused_scales_bytes(depth));
+    uint32_t* wimg = reinterpret_cast<uint32_t*>(base + fused_scales_bytes(depth) + fused_bias_bytes(depth));
+    float2* xg = reinterpret_cast<float2*>(base + fused_scales_bytes(depth) + fused_bias_bytes(depth) + fused_image_only_bytes(depth));
     // The CTAs of a group wait for each other, so all of them must be resident: cooperative launch, one CTA per SM.
     static int max_groups_of[64] = {0};                       // per device (function attributes are per context)
     int dev = 0;
@@ -718,6 +774,7 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
     if (dev < 0 || dev >= 64) return DCD_E_DEVICE;
     if (max_groups_of[dev] == 0) {
         cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+        cudaFuncSetAttribute(fused_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CH * CH * sizeof(float)));
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_fused_kernel, FTHREADS, kFusedSmem);
@@ -728,14 +785,15 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
         max_groups_of[dev] = g;
     }
     const int max_groups = max_groups_of[dev];
-    float2* xg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(wimg) + (size_t)2 * depth * 3 * CH * CH * sizeof(uint32_t));
+    fused_prep_kernel<<<4 * depth, 256, CH * CH * sizeof(float), st>>>(params4, params6, depth, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;
     const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);
     MlpArgs args = a;
-    const float2* scales_arg = scales;
+    const float2* scales_arg = scales2;
+    const float* bias_arg = bias2;
     const uint32_t* wimg_arg = wimg;
-    void* kargs[] = {&args, &scales_arg, &wimg_arg, &xg};
+    void* kargs[] = {&args, &scales_arg, &bias_arg, &wimg_arg, &xg};
     if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mlp_fused_kernel), dim3(FCS * ngroups), dim3(FTHREADS), kargs, kFusedSmem,
                                     st) != cudaSuccess) {
         cudaGetLastError();

@@ -458,8 +458,7 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
 // bytes appended to the MLP workspace for the per-matrix FP16 scales (scale, 1/scale)
 bool gmw_fused_supported(int n);
 size_t gmw_fused_image_bytes(int depth);
-int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, const float2* scales,
-                         uint32_t* wimg, cudaStream_t st);
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st);
 
 static size_t tc_scales_bytes(int depth) { return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256; }
 // bytes appended to the MLP workspace: per-matrix FP16 scales (scale, 1/scale) + the pre-split weight image
@@ -487,17 +486,16 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     // the scales live right after the layout's own area (256-byte aligned)
     float2* scales = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ws) +
                                                (((size_t)a.L.total * sizeof(float) + 255) / 256) * 256);
-    tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
     const unsigned g2 = (unsigned)(((a.L.E + 255) / 256) * N);
     if (!save && gmw_fused_supported(n) && !force_layerwise()) {
         // inference: whole network on chip, one kernel (gmw_mlp_fused.cu)
-        uint32_t* wimg = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth));
-        const int rc = launch_gmw_fused_fwd(a, params4, params6, scales, wimg, st);
+        const int rc = launch_gmw_fused_fwd(a, params4, params6, reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth), st);
         if (rc != DCD_OK) return rc;
         gmw_edge_weight_kernel<true><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
         DCD_CHECK_LAUNCH();
         return DCD_OK;
     }
+    tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);

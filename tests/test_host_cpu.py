@@ -50,8 +50,9 @@ def test_version_strerror_and_size_queries(lib):
     E, T = 2628, 21
     acts_and_stats = 4 * (2 * 3 * 128 * T * 128 + 2 * 12 * 2 * T * 128 * 2)
     scales = 768                                         # 72 per-matrix (scale, 1/scale) pairs, 256-byte aligned
-    image = 72 * 128 * 128 * 4                           # pre-split FP16 hi/lo weight image of the fused forward
-    image += 32 * 2 * 8 * 128 * 8                        # + its statistics exchange buffer [group][slot][rank][128] float2
+    # tail of the fused forward: 48 matrices (folded preconv.conv1 and conv2 per block and net): scales, biases, pre-split
+    # FP16 hi/lo weight image; then the statistics exchange buffer [group][slot][rank][128] float2
+    image = 512 + 48 * 128 * 4 + 48 * 128 * 128 * 4 + 32 * 2 * 8 * 128 * 8
     assert lib.dcd_gmw_workspace_bytes(1, 73, 12, 0) == acts_and_stats + scales + image
     assert lib.dcd_gmw_workspace_bytes(0, 73, 12, 0) == 0
     assert lib.dcd_gmw_workspace_bytes(8, 73, 12, 1) > lib.dcd_gmw_workspace_bytes(8, 73, 12, 0)
