@@ -196,11 +196,11 @@ __device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, u
 // Per matrix m = (net, block, j) with j = 0: Wf, j = 1: W2 this kernel writes the power-of-two FP16 scale, the bias
 // and the pre-split weight image [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1) of
 // scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
-__global__ void __launch_bounds__(256) fused_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
+__global__ void __launch_bounds__(1024) fused_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
                                                          float2* __restrict__ scales2, float* __restrict__ bias2,
                                                          uint32_t* __restrict__ img) {
     extern __shared__ float wf_s[];                           // [in][out] FP32, 64 KB
-    __shared__ float red[8];
+    __shared__ float red[32];
     __shared__ float scale_s;
     const int m = blockIdx.x;
     const int j = m & 1, blk = (m >> 1) % depth, net = m / (2 * depth);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(const float* __restrict
         const float* Wp = prm + blob_w(cin, blk, 0);          // [in][mid]
         const float* W1 = prm + blob_w(cin, blk, 1);          // [mid][out]
         const int o = tid & 127;
-        for (int i = tid >> 7; i < CH; i += 2) {
+        for (int i = tid >> 7; i < CH; i += 8) {
             double acc = 0.0;
             for (int k = 0; k < CH; ++k) acc = fma((double)Wp[i * CH + k], (double)W1[k * CH + o], acc);
             wf_s[i * CH + o] = (float)acc;
@@ -224,19 +224,19 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(const float* __restrict
         }
     } else {
         const float* W2 = prm + blob_w(cin, blk, 2);
-        for (int i = tid; i < CH * CH; i += 256) wf_s[i] = W2[i];
+        for (int i = tid; i < CH * CH; i += 1024) wf_s[i] = W2[i];
         if (tid < CH) bias2[m * CH + tid] = prm[blob_b(cin, blk, 2) + tid];
     }
     __syncthreads();
     // per-matrix power-of-two scale that puts max|W| in [512, 1024): FP16 hi/lo both stay normal
     float mx = 0.f;
-    for (int i = tid; i < CH * CH; i += 256) mx = fmaxf(mx, fabsf(wf_s[i]));
+    for (int i = tid; i < CH * CH; i += 1024) mx = fmaxf(mx, fabsf(wf_s[i]));
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
         mx = 0.f;
-        for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        for (int w = 0; w < 32; ++w) mx = fmaxf(mx, red[w]);
         int e = 0;
         if (mx > 0.f) frexpf(mx, &e);
         scales2[m] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) fused_prep_kernel(const float* __restrict
     __syncthreads();
     const float scale = scale_s;
     uint32_t* out = img + (size_t)m * CH * CH;
-    for (int idx = tid; idx < CH * 64; idx += 256) {
+    for (int idx = tid; idx < CH * 64; idx += 1024) {
         const int row = idx & 127, c = idx >> 7;
         const float w0 = wf_s[(2 * c) * CH + row] * scale, w1 = wf_s[(2 * c + 1) * CH + row] * scale;
         const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
@@ -785,7 +785,7 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
         max_groups_of[dev] = g;
     }
     const int max_groups = max_groups_of[dev];
-    fused_prep_kernel<<<4 * depth, 256, CH * CH * sizeof(float), st>>>(params4, params6, depth, scales2, bias2, wimg);
+    fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;
     const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);
