@@ -339,6 +339,17 @@ def main():
     ms_sel = time_kernel(lambda: check(L.dcd_edge_select_fwd(ptr(d_kps), ptr(d_k3), ptr(d_rot), ptr(d_K), 0, sel_n, N_KPTS, K_SEL,
                                                              2.0, 80.0, 3, ptr(idx_b), ptr(z_b), 0, 0, st), "select"), reps=5)
     del edges
+    # frame epilogue: image-space keypoints -> edge solve + mean -> 3D location, one launch
+    pad_o = torch.tensor([19.0, 5.0], device=dev).expand(N, 2).contiguous()
+    ctr = (d_kps.mean(1) + pad_o) / 4
+    pts_o = ctr.floor()
+    ofs_o = (ctr - pts_o).contiguous()
+    off_o = ((d_kps + pad_o.unsqueeze(1)) / 4 - ctr.unsqueeze(1)).contiguous()
+    dims_o = torch.stack((torch.full((N,), 3.9, device=dev), -d_k3[:, -1, 1], torch.full((N,), 1.6, device=dev)), dim=1).contiguous()
+    loc_o = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    ms_loc = time_kernel(lambda: check(L.dcd_dgde_locate_fwd(ptr(off_o), ptr(d_k3), ptr(d_rot), ptr(d_K), ptr(pts_o), ptr(ofs_o),
+                                                             ptr(pad_o), ptr(dims_o), 0, N, N_KPTS, 2.0, 80.0, 3, 4.0, ptr(mean),
+                                                             ptr(loc_o), st), "locate"))
 
     # ---- GMW training step, batch 8 per GPU (BASELINE configs[2]): compute_z + forward (saved) + loss + backward
     tb = 8
@@ -412,6 +423,11 @@ def main():
                 "dgde_solve_edges": {"objects_per_s": N / (ms_edges * 1e-3), "ms": ms_edges,
                                      "hbm_gbs": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9,
                                      "frac_hbm": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "dgde_frame_epilogue": {"objects_per_s": N / (ms_loc * 1e-3), "ms": ms_loc,
+                                        "fp32_tflops": F_SOLVE * N / (ms_loc * 1e-3) / 1e12,
+                                        "hbm_gbs": (B_SOLVE + 52) * N / (ms_loc * 1e-3) / 1e9,
+                                        "what": "keypoint offsets -> image keypoints -> edge solve + mean -> 3D location "
+                                                "(detector_infer.py:215-227,186-188), one launch"},
                 "edge_select_top1500": {"objects_per_s": sel_n / (ms_sel * 1e-3), "ms": ms_sel, "objects": sel_n},
                 "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": tb * world / (ms_train * 1e-3),
                                       "what": "configs[2]: compute_z + edge MLP fwd + softmax aggregate + L1 loss + full backward (all GEMMs on "

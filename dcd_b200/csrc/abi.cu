@@ -15,6 +15,8 @@ int launch_gmw_aggregate_bwd(const float*, const float*, const int64_t*, int64_t
                              float*, float*, cudaStream_t);
 int launch_gmw_weights_fwd(const float*, const float*, const float*, const float*, int64_t, int, int, int, float*,
                            float*, float*, float*, cudaStream_t);
+int launch_dgde_locate(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                       const float*, const float*, int64_t, int, float, float, int, float, float*, float*, cudaStream_t);
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
 size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
@@ -84,6 +86,18 @@ int dcd_edge_solve_bwd(const float* kps, const float* kps3d, const float* rot, c
     if (misaligned(kps, 8) || misaligned(grad_kps, 8)) return DCD_E_INVALID;
     return launch_edge_solve_bwd(kps, kps3d, rot, K, N, n, lo, hi, flags, idx, k, grad_depth, grad_mean, grad_kps,
                                  grad_kps3d, (cudaStream_t)stream);
+}
+
+int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* rot, const float* K, const float* points,
+                        const float* offsets, const float* pad, const float* dims, const float* depth_in, int64_t N, int n,
+                        float lo, float hi, int flags, float down_ratio, float* depth_out, float* locations, void* stream) {
+    if (N < 0) return DCD_E_INVALID;
+    if (kpts_off && bad_n(n)) return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!K || !points || !offsets || !pad || (!depth_out && !locations)) return DCD_E_INVALID;
+    if (kpts_off ? (!kps3d || !rot) : !depth_in) return DCD_E_INVALID;
+    return launch_dgde_locate(kpts_off, kps3d, rot, K, points, offsets, pad, dims, depth_in, N, kpts_off ? n : 2, lo, hi, flags,
+                              down_ratio, depth_out, locations, (cudaStream_t)stream);
 }
 
 size_t dcd_gmw_param_count(int cin, int depth) { return (size_t)blob_size(cin, depth); }

@@ -1,0 +1,110 @@
+// Frame epilogue of the DGDE detector head around the edge solve, one kernel:
+//   image-space keypoints   real_2d = (kpts_off + (points + offsets)) * down_ratio - pad       detector_infer.py:216-217
+//   edge solve + mean       depth   = mean_e clamp(|H| / max(|V|, 1e-10), lo, hi) - b3          anno_encoder.py:326-390, :225
+//   3D location             (u, v)  = (points + offsets) * down_ratio - pad                      anno_encoder.py:147-161
+//                           x = ((u - c_u) * depth) / f_u + b_x,  y likewise,  z = depth         kitti_utils.py:239-244, 399-417
+//                           y += h / 2                                                           detector_infer.py:188
+// so the 2D keypoints never exist in global memory and the location needs no second launch.
+// One warp per object, same staging as the throughput edge-solve kernel (edge_solve.cu): 16-byte per-keypoint
+// terms in shared memory, (i, j) byte offsets from a CTA-shared pair table, per-lane strided accumulation.
+// Every operation is rounded like the reference's FP32 torch sequence; the calibration scalars b_x, b_y are formed
+// in FP32 from the FP32 matrix (the reference forms them in float64 numpy: a 1-ulp difference of a 0.06 m offset).
+#include "dcd_common.cuh"
+
+namespace dcd {
+namespace {
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+dgde_locate_warp_kernel(const float* __restrict__ kpts_off, const float* __restrict__ kps3d, const float* __restrict__ rot,
+                        const float* __restrict__ K, const float* __restrict__ points, const float* __restrict__ offsets,
+                        const float* __restrict__ pad, const float* __restrict__ dims, const float* __restrict__ depth_in,
+                        int64_t N, int n, float lo, float hi, int flags, float down_ratio,
+                        float* __restrict__ depth_out, float* __restrict__ loc_out) {
+    constexpr int NWARP = THREADS / 32;
+    const int E = n * (n - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* kp_all = reinterpret_cast<float4*>(smem_raw);                     // [NWARP][n]
+    uint32_t* tab_s = reinterpret_cast<uint32_t*>(kp_all + NWARP * n);        // [E] byte offsets (i*16) | (j*16) << 16
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool solve = kpts_off != nullptr;
+    if (solve) {
+        for (int e = tid; e < E; e += THREADS) {
+            int i, j;
+            decode_edge(e, n, i, j);
+            tab_s[e] = (uint32_t)(i * 16) | ((uint32_t)(j * 16) << 16);
+        }
+    }
+    __syncthreads();
+    float4* kp = kp_all + warp * n;
+    const unsigned char* kpb = reinterpret_cast<const unsigned char*>(kp);
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    for (int64_t obj = (int64_t)blockIdx.x * NWARP + warp; obj < N; obj += (int64_t)gridDim.x * NWARP) {
+        const float* Ko = K + obj * 12;
+        const float f_u = __ldg(Ko + 0), c_u = __ldg(Ko + 2), f_v = __ldg(Ko + 5), c_v = __ldg(Ko + 6);
+        const float cx = __fadd_rn(__ldg(points + obj * 2), __ldg(offsets + obj * 2));
+        const float cyy = __fadd_rn(__ldg(points + obj * 2 + 1), __ldg(offsets + obj * 2 + 1));
+        const float pad_u = __ldg(pad + obj * 2), pad_v = __ldg(pad + obj * 2 + 1);
+        float depth;
+        if (solve) {
+            const float b3 = (flags & DCD_SUB_B3) ? __ldg(Ko + 11) : 0.f;
+            const float r = __ldg(rot + obj);
+            const float sn = sinf(r), cs = cosf(r);
+            for (int t = lane; t < n; t += 32) {
+                const float off_v = __ldg(kpts_off + (obj * n + t) * 2 + 1);
+                const float v_img = __fsub_rn(__fmul_rn(__fadd_rn(off_v, cyy), down_ratio), pad_v);
+                const float* p3 = kps3d + (obj * n + t) * 3;
+                kp[t] = keypoint_terms(v_img, __ldg(p3), __ldg(p3 + 1), __ldg(p3 + 2), sn, cs, normalise, c_v, f_v);
+            }
+            __syncwarp();
+            float acc = 0.f;
+            for (int e = lane; e < E; e += 32) {
+                const uint32_t p = tab_s[e];
+                const float4 a = *reinterpret_cast<const float4*>(kpb + (p & 0xffffu));
+                const float4 b = *reinterpret_cast<const float4*>(kpb + (p >> 16));
+                acc += edge_depth(a, b, lo, hi, b3);
+            }
+            acc = warp_sum(acc);
+            depth = __fdiv_rn(acc, (float)E);
+            __syncwarp();                                    // all lanes done with kp before it is restaged
+        } else {
+            depth = __ldg(depth_in + obj);
+        }
+        if (lane == 0) {
+            if (depth_out != nullptr) depth_out[obj] = depth;
+            if (loc_out != nullptr) {
+                const float u = __fsub_rn(__fmul_rn(cx, down_ratio), pad_u);
+                const float v = __fsub_rn(__fmul_rn(cyy, down_ratio), pad_v);
+                const float b_x = __fdiv_rn(__ldg(Ko + 3), -f_u), b_y = __fdiv_rn(__ldg(Ko + 7), -f_v);
+                float x = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(u, c_u), depth), f_u), b_x);
+                float y = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(v, c_v), depth), f_v), b_y);
+                if (dims != nullptr) y = __fadd_rn(y, __fmul_rn(__ldg(dims + obj * 3 + 1), 0.5f));
+                loc_out[obj * 3 + 0] = x;
+                loc_out[obj * 3 + 1] = y;
+                loc_out[obj * 3 + 2] = depth;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_dgde_locate(const float* kpts_off, const float* kps3d, const float* rot, const float* K, const float* points,
+                       const float* offsets, const float* pad, const float* dims, const float* depth_in, int64_t N, int n,
+                       float lo, float hi, int flags, float down_ratio, float* depth_out, float* loc_out, cudaStream_t st) {
+    constexpr int T = 256;
+    const int E = n * (n - 1) / 2;
+    const size_t smem = (size_t)(T / 32) * n * sizeof(float4) + (size_t)E * sizeof(uint32_t);
+    if (smem > 227 * 1024) return DCD_E_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(dgde_locate_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t want = (N + T / 32 - 1) / (T / 32);
+    const int64_t cap = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    dgde_locate_warp_kernel<T><<<grid, T, smem, st>>>(kpts_off, kps3d, rot, K, points, offsets, pad, dims, depth_in, N, n, lo, hi,
+                                                      flags, down_ratio, depth_out, loc_out);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

@@ -193,6 +193,71 @@ def edge_depth_mean(kps, kps_3d, rot_y, K, training=False, num_k: int = K_SEL) -
     return _EdgeSelectSolve.apply(kps, kps_3d, rot, K, None, lo, hi, flags, num_k, True)[3]
 
 
+DOWN_RATIO = 4.0    # MODEL.BACKBONE.DOWN_RATIO of the reference; hard-coded `*4` at detector_infer.py:217
+
+
+def _calib_per_object(P, N, dev):
+    """[3,4] / [N,3,4] torch or numpy projection matrix (float64 in the reference) -> contiguous FP32 [N,3,4]."""
+    P = torch.as_tensor(P)
+    if P.dim() == 2:
+        P = P.unsqueeze(0).expand(N, -1, -1)
+    return f32c(P.to(dev))
+
+
+def _pad_per_object(pad_size, batch_idxs, N, dev):
+    pad = torch.as_tensor(pad_size, dtype=torch.float32, device=dev)
+    if pad.dim() == 1:
+        return pad.reshape(1, 2).expand(N, 2).contiguous()
+    if batch_idxs is not None:
+        return pad[batch_idxs.to(dev).long()].contiguous()
+    if pad.shape[0] == 1:
+        return pad.expand(N, 2).contiguous()
+    return f32c(pad)
+
+
+def compute_pairs_kpts_depth(pred_extra_kpts_2d, pred_bbox_points, pred_offset_3D, pad_size, pred_extra_kpts_3d, pred_rots, P,
+                             batch_idxs=None, dims=None, return_locations: bool = False):
+    """Fused form of PostProcessor.compute_pairs_kpts_depth (DGDE/model/head/detector_infer.py:215-227): the image-space
+    keypoints `(kpts + (points + offsets)) * 4 - pad_size` are formed on the fly, solved over all keypoint pairs and
+    averaged -> depth [N].  With `return_locations` also the object's 3D location (decode_location_flatten,
+    anno_encoder.py:147-161, and `+ h / 2` on y when `dims` [N,3] is given, detector_infer.py:186-188) from the same launch.
+    P: the image's 3x4 projection matrix (or one per object), pad_size: [2], [1,2], or [B,2] with batch_idxs."""
+    require_cuda(pred_extra_kpts_2d, pred_extra_kpts_3d, pred_rots, pred_bbox_points, pred_offset_3D)
+    off, k3 = f32c(pred_extra_kpts_2d), f32c(pred_extra_kpts_3d)
+    rot = f32c(pred_rots).reshape(-1)
+    N, n = off.shape[0], off.shape[1]
+    dev = off.device
+    K = _calib_per_object(P, N, dev)
+    _check_shapes(off, k3, rot, K)
+    pts, ofs = f32c(pred_bbox_points), f32c(pred_offset_3D)
+    pad = _pad_per_object(pad_size, batch_idxs, N, dev)
+    d3 = f32c(dims) if dims is not None else None
+    depth = torch.empty((N,), dtype=torch.float32, device=dev)
+    loc = torch.empty((N, 3), dtype=torch.float32, device=dev) if return_locations else None
+    lo, hi = DGDE_CLAMP
+    if N:
+        check(_lib.lib().dcd_dgde_locate_fwd(ptr(off), ptr(k3), ptr(rot), ptr(K), ptr(pts), ptr(ofs), ptr(pad),
+                                             ptr(d3) if d3 is not None else 0, 0, N, n, lo, hi,
+                                             FLAG_NORMALISE_2D | FLAG_SUB_B3, DOWN_RATIO, ptr(depth),
+                                             ptr(loc) if loc is not None else 0, stream_ptr()), "dcd_dgde_locate_fwd")
+    return (depth, loc) if return_locations else depth
+
+
+def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=None):
+    """Anno_Encoder.decode_location_flatten (DGDE/model/anno_encoder.py:147-161) with the calibration given as the
+    3x4 matrix of the image ([3,4]) or per object ([N,3,4]) instead of Calibration objects -> locations [N,3]."""
+    require_cuda(points, offsets, depths)
+    pts, ofs, dep = f32c(points), f32c(offsets), f32c(depths).reshape(-1)
+    N, dev = pts.shape[0], pts.device
+    K = _calib_per_object(P, N, dev)
+    pad = _pad_per_object(pad_size, batch_idxs, N, dev)
+    loc = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    if N:
+        check(_lib.lib().dcd_dgde_locate_fwd(0, 0, 0, ptr(K), ptr(pts), ptr(ofs), ptr(pad), 0, ptr(dep), N, 2, 0.0, 0.0, 0,
+                                             DOWN_RATIO, 0, ptr(loc), stream_ptr()), "dcd_dgde_locate_fwd")
+    return loc
+
+
 def compute_z(kpts_2d, kpts_3d, pred_rot, num_k: int = K_SEL) -> Tuple[torch.Tensor, torch.Tensor]:
     """Drop-in for GMW/main.py:373-416: (Z_v_raw [b,E] clamped to [0.1,80], good_idx [b,1500] int64)."""
     require_cuda(kpts_2d, kpts_3d, pred_rot)

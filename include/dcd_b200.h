@@ -76,6 +76,22 @@ int dcd_edge_select_fwd(const float* kps, const float* kps3d, const float* rot, 
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Frame epilogue of the detector head around the edge solve, fused:
+ *   image-space keypoints  (kpts_off + (points + offsets)) * down_ratio - pad     DGDE/model/head/detector_infer.py:216-217
+ *   edge solve + mean over the edges (inference form of decode_pairs_kpts_depth)  DGDE/model/anno_encoder.py:326-390, detector_infer.py:225
+ *   location = project_image_to_rect((points + offsets) * down_ratio - pad, depth) anno_encoder.py:147-161, kitti_utils.py:239-244,399-417
+ *   location.y += dims[:, 1] / 2 when dims != NULL                                 detector_infer.py:188
+ * kpts_off [N,n,2] keypoint regression offsets (feature-map units), points / offsets [N,2] (heat-map peak and its
+ * sub-pixel offset), pad [N,2] (pad_size[batch_idxs]), K [N,3,4] (required), dims [N,3] (l,h,w) or NULL.
+ * kpts_off == NULL: no solve, the depths are read from depth_in [N] (the reference's first decode_location_flatten
+ * call with the ensemble depth, detector_infer.py:175-176).  Outputs: depth_out [N] and/or locations [N,3].
+ */
+int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* rot, const float* K,
+                        const float* points, const float* offsets, const float* pad, const float* dims,
+                        const float* depth_in, int64_t N, int n, float lo, float hi, int flags, float down_ratio,
+                        float* depth_out, float* locations, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Edge solve, backward (the autograd of decode_pairs_kpts_depth, consumers detector_loss.py:188-214,
  * :388-396).  grad_depth is [N,k] when idx != NULL (gradient of the selected depths) or [N,E] when
  * idx == NULL; grad_mean [N] (may be NULL) is the gradient of depth_mean and is spread as g/k (or g/E).

@@ -22,6 +22,7 @@ from __future__ import annotations
 import math
 from typing import Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -273,6 +274,73 @@ def dgde_pipeline(kps, kps_3d, rot_y, K, faithful: bool = False):
     """DGDE inference: decode_pairs_kpts_depth(training=False) + mean (detector_infer.py:222-225)."""
     d, _ = decode_pairs_kpts_depth(kps, kps_3d, rot_y, K, training=False, faithful=faithful)
     return d.mean(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Frame epilogue around the DGDE edge solve (SURVEY 8f rows N2 / N4): image-space keypoints from the
+# regression channels, then the object's 3D location from the solved depth.
+# ---------------------------------------------------------------------------------------------
+DOWN_RATIO = 4      # DGDE/config/defaults.py (MODEL.BACKBONE.DOWN_RATIO); hard-coded `*4` at detector_infer.py:217
+
+
+def decode_kpts_2d_img(kpts_off, points, offsets, pad_size, down_ratio=DOWN_RATIO):
+    """DGDE/model/head/detector_infer.py:216-217 (`compute_pairs_kpts_depth`, `generate_infer_data`):
+    real_pred_2d = (pred_extra_kpts_2d + (pred_bbox_points + pred_offset_3D)[:, None]) * 4 - pad_size.
+    kpts_off [N,n,2], points/offsets [N,2], pad_size [2] or [N,2] -> [N,n,2]."""
+    centre = (points + offsets).unsqueeze(1).expand_as(kpts_off)
+    pad = pad_size if pad_size.dim() == 1 else pad_size.unsqueeze(1)
+    return (kpts_off + centre) * down_ratio - pad
+
+
+def calib_scalars(P):
+    """DGDE/data/datasets/kitti_utils.py:239-244: intrinsics of a 3x4 projection matrix, computed in the
+    matrix' own precision (the reference holds P as numpy float64)."""
+    P = np.asarray(P)
+    c_u, c_v, f_u, f_v = P[0, 2], P[1, 2], P[0, 0], P[1, 1]
+    return c_u, c_v, f_u, f_v, P[0, 3] / (-f_u), P[1, 3] / (-f_v)
+
+
+def project_image_to_rect(uv_depth, P):
+    """kitti_utils.py:399-417 on a torch tensor [n,3] (u, v, depth) -> rect camera coordinates [n,3]."""
+    c_u, c_v, f_u, f_v, b_x, b_y = (float(x) for x in calib_scalars(P))
+    x = ((uv_depth[:, 0] - c_u) * uv_depth[:, 2]) / f_u + b_x
+    y = ((uv_depth[:, 1] - c_v) * uv_depth[:, 2]) / f_v + b_y
+    out = torch.zeros_like(uv_depth)
+    out[:, 0] = x
+    out[:, 1] = y
+    out[:, 2] = uv_depth[:, 2]
+    return out
+
+
+def decode_location_flatten(points, offsets, depths, Ps, pad_size, batch_idxs, down_ratio=DOWN_RATIO):
+    """DGDE/model/anno_encoder.py:147-161.  Ps: one 3x4 matrix per image of the batch, pad_size [B,2],
+    batch_idxs [N] int64 -> locations [N,3]."""
+    gts = torch.unique(batch_idxs, sorted=True).tolist()
+    locations = points.new_zeros(points.shape[0], 3).float()
+    pts = (points + offsets) * down_ratio - pad_size[batch_idxs]
+    for gt in gts:
+        sel = torch.nonzero(batch_idxs == gt).squeeze(-1)
+        locations[sel] = project_image_to_rect(torch.cat((pts[sel], depths[sel, None]), dim=1), Ps[gt])
+    return locations
+
+
+def compute_pairs_kpts_depth(kpts_off, points, offsets, pad_size, kps_3d, rot_y, K, faithful=False):
+    """detector_infer.py:215-227: image-space keypoints -> edge solve (inference form) -> mean over the edges."""
+    real_2d = decode_kpts_2d_img(kpts_off, points, offsets, pad_size)
+    d, _ = decode_pairs_kpts_depth(real_2d, kps_3d, rot_y, K, training=False, faithful=faithful)
+    return d.mean(1)
+
+
+def frame_locations(kpts_off, points, offsets, pad_size, kps_3d, rot_y, P, dims):
+    """detector_infer.py:186-192 for one image: edge depths -> decode_location_flatten -> y += h / 2.
+    P [3,4] (numpy float64 like the reference's calib.P), pad_size [1,2], dims [N,3] (l, h, w)."""
+    N = kpts_off.shape[0]
+    K = torch.from_numpy(np.asarray(P)).unsqueeze(0).expand(N, -1, -1)       # float64, stride 0 (detector_infer.py:221)
+    depth = compute_pairs_kpts_depth(kpts_off, points, offsets, pad_size.reshape(-1)[:2], kps_3d, rot_y, K)
+    batch_idxs = torch.zeros(N, dtype=torch.int64)
+    loc = decode_location_flatten(points, offsets, depth, [P], pad_size.reshape(1, 2), batch_idxs)
+    loc[:, 1] += dims[:, 1] / 2
+    return depth, loc
 
 
 def random_state_dict(seed: int, depth: int = NET_DEPTH, dtype=torch.float32) -> Dict[str, torch.Tensor]:

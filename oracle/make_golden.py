@@ -164,6 +164,69 @@ def gmw_fixture(name, N, seed, wseed):
     print(name, "ref fwd %.2fs bwd %.2fs" % (t_fwd, t_bwd), "diag-vs-full rel", rel, "oracle grad worst rel", worst)
 
 
+def frame_inputs(ob, seed, pad=(19.0, 5.0)):
+    """Detector-head form of synthetic objects (one image): heat-map peak `points` (integer feature-map pixel),
+    sub-pixel `offsets`, per-keypoint offsets such that (kpts_off + points + offsets) * 4 - pad reproduces ob.kps,
+    and the (l, h, w) dimensions the template was drawn with."""
+    g = torch.Generator().manual_seed(seed)
+    pad_t = torch.tensor([pad], dtype=torch.float32)
+    centre = (ob.kps.mean(1) + pad_t) / 4                      # somewhere inside the object, feature-map units
+    points = centre.floor()
+    offsets = centre - points + 0.1 * (torch.rand(centre.shape, generator=g) - 0.5)
+    kpts_off = (ob.kps + pad_t) / 4 - (points + offsets).unsqueeze(1)
+    h = -ob.kps_3d[:, -1, 1]                                   # top centre of the template sits at y = -h
+    dims = torch.stack((ob.kps_3d[:, -10, 0].abs() * 2, h, ob.kps_3d[:, -10, 2].abs() * 2), dim=1)
+    return kpts_off.contiguous(), points.contiguous(), offsets.contiguous(), pad_t, dims.contiguous()
+
+
+def load_reference_calibration(P):
+    """The reference's own Calibration (DGDE/data/datasets/kitti_utils.py:206-244) on a temporary KITTI calib file."""
+    import importlib.util
+    import tempfile
+    rl._stub_matplotlib()
+    spec = importlib.util.spec_from_file_location(
+        "ref_kitti_utils", os.path.join(rl.REFERENCE_ROOT, "DGDE", "data", "datasets", "kitti_utils.py"))
+    ku = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ku)
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        for key in ("P2", "P3"):
+            f.write(key + ": " + " ".join(repr(float(x)) for x in np.asarray(P).reshape(-1)) + "\n")
+        f.write("R0_rect: 1 0 0 0 1 0 0 0 1\n")
+        f.write("Tr_velo_to_cam: 1 0 0 0 0 1 0 0 0 0 1 0\n")
+        path = f.name
+    calib = ku.Calibration(path)
+    os.unlink(path)
+    return calib
+
+
+def locate_fixture(name, N, n, seed):
+    """Frame epilogue: detector_infer.py:215-227 + :186-192 with the reference's own
+    decode_pairs_kpts_depth, decode_location_flatten and Calibration.project_image_to_rect."""
+    enc = rl.load_dgde_anno_encoder()
+    enc.down_ratio = O.DOWN_RATIO
+    ob = synth.make_objects(N=N, n=n, seed=seed)
+    P = np.array(synth.P2, dtype=np.float64)
+    calib = load_reference_calibration(P)
+    kpts_off, points, offsets, pad, dims = frame_inputs(ob, seed)
+    # --- reference, line by line
+    real_2d = (kpts_off + (points + offsets).unsqueeze(1).expand_as(kpts_off)) * 4 - pad          # :216-217
+    Calib_P = torch.from_numpy(calib.P).unsqueeze(0).expand(N, -1, -1)                               # :221
+    pairs, _ = enc.decode_pairs_kpts_depth(real_2d, ob.kps_3d, ob.rot_y, Calib_P)                    # :222
+    depth = pairs.mean(1)                                                                            # :225
+    bi = depth.new_zeros(N).long()                                                                   # :186
+    loc = enc.decode_location_flatten(points, offsets, depth, [calib], pad, bi)                      # :187
+    loc[:, 1] += dims[:, 1] / 2                                                                      # :188
+    # --- oracle restatement
+    assert torch.equal(O.decode_kpts_2d_img(kpts_off, points, offsets, pad.reshape(-1)), real_2d)
+    d_o, loc_o = O.frame_locations(kpts_off, points, offsets, pad, ob.kps_3d, ob.rot_y, P, dims)
+    assert torch.equal(d_o, depth) and torch.equal(loc_o, loc), "oracle != reference (frame epilogue)"
+    assert float((real_2d - ob.kps).abs().max()) < 1e-3
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kpts_off=npy(kpts_off), points=npy(points), offsets=npy(offsets),
+                        pad=npy(pad), dims=npy(dims), kps_3d=npy(ob.kps_3d), rot_y=npy(ob.rot_y), P=P,
+                        real_2d=npy(real_2d), depth=npy(depth), locations=npy(loc), gt_depth=npy(ob.gt_depth))
+    print(name, "frame epilogue: depth err vs gt (median rel) %.4f" % float(((depth - ob.gt_depth).abs() / ob.gt_depth).median()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -173,6 +236,8 @@ def main():
     dgde_fixture("dgde_n8_N7", N=7, n=8, seed=synth.BASE_SEED + 12)         # E=28 < 1500: inference only
     dgde_fixture("dgde_n256_N4", N=4, n=256, seed=synth.BASE_SEED + 4)      # BASELINE configs[4]
     gmw_fixture("gmw_n73_N4", N=4, seed=synth.BASE_SEED + 3, wseed=7)
+    locate_fixture("locate_n73_N50", N=50, n=73, seed=synth.BASE_SEED + 20)   # one full frame
+    locate_fixture("locate_n20_N7", N=7, n=20, seed=synth.BASE_SEED + 21)
 
 
 if __name__ == "__main__":

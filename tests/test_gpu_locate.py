@@ -1,0 +1,86 @@
+"""GPU parity of the detector-head frame epilogue through the C ABI:
+image-space keypoints -> edge solve -> mean depth -> 3D location, against the reference-generated fixtures
+(`oracle/make_golden.py::locate_fixture`: unmodified decode_pairs_kpts_depth, decode_location_flatten and
+Calibration.project_image_to_rect) and against the oracle on other shapes.
+
+Bars: depth rel <= 1e-5 (the north-star's depth tolerance; CPU and GPU differ by the rounding of sin/cos and of the
+mean's summation order); locations abs <= 1e-4 m + rel 1e-5 (x, y scale with depth; b_x, b_y are formed in FP32 here and
+in float64 by the reference).  The fused depth equals `edge_depth_mean` on the materialised keypoints to 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+import dcd_b200
+from dcd_b200 import synth
+from oracle import dcd_oracle as O
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(*ts):
+    return [t.to(DEV) if torch.is_tensor(t) else t for t in ts]
+
+
+@pytest.mark.parametrize("name", ["locate_n73_N50", "locate_n20_N7"])
+def test_frame_epilogue_vs_reference_fixture(golden, name):
+    G = golden(name)
+    off, pts, ofs, pad, dims, k3, rot = cu(G["kpts_off"], G["points"], G["offsets"], G["pad"], G["dims"], G["kps_3d"], G["rot_y"])
+    P = G["P"]
+    depth, loc = dcd_b200.compute_pairs_kpts_depth(off, pts, ofs, pad, k3, rot, P, dims=dims, return_locations=True)
+    assert depth.shape == (off.shape[0],) and loc.shape == (off.shape[0], 3)
+    assert rel_err(depth.cpu(), G["depth"]) < 1e-5
+    ref = G["locations"]
+    assert bool(((loc.cpu() - ref).abs() <= 1e-4 + 1e-5 * ref.abs()).all())
+    assert torch.equal(loc[:, 2], depth)
+    # depth only, and the un-fused route through the materialised image-space keypoints
+    d_only = dcd_b200.compute_pairs_kpts_depth(off, pts, ofs, pad, k3, rot, P)
+    assert torch.equal(d_only, depth)
+    real_2d = G["real_2d"].to(DEV)
+    K = torch.as_tensor(P).unsqueeze(0).expand(off.shape[0], -1, -1).to(DEV)          # float64, stride 0 (detector_infer.py:221)
+    unfused = dcd_b200.edge_depth_mean(real_2d, k3, rot, K)
+    assert rel_err(depth, unfused) < 1e-6
+    # decode_location_flatten on its own (the reference's first call, with the ensemble depth): same kernel, no solve
+    bi = torch.zeros(off.shape[0], dtype=torch.int64, device=DEV)
+    loc2 = dcd_b200.decode_location_flatten(pts, ofs, depth, P, pad, bi)
+    loc2[:, 1] += dims[:, 1] / 2
+    assert torch.allclose(loc2, loc, rtol=0, atol=1e-6)
+
+
+def test_frame_epilogue_vs_oracle_batched_frames():
+    """Several images in one call: per-object calibration and pad (pad_size[batch_idxs]), ragged object counts."""
+    counts = torch.tensor([3, 50, 1, 17], dtype=torch.int64)
+    ob = synth.make_objects(n=73, seed=77, counts=counts, jitter_fx=0.02)
+    N = ob.N
+    g = torch.Generator().manual_seed(5)
+    pad_b = torch.tensor([[19.0, 5.0], [0.0, 0.0], [7.0, 3.0], [12.0, 8.0]])
+    pad = pad_b[ob.frame_id]
+    centre = (ob.kps.mean(1) + pad) / 4
+    pts = centre.floor()
+    ofs = centre - pts + 0.05 * (torch.rand(centre.shape, generator=g) - 0.5)
+    off = (ob.kps + pad.unsqueeze(1)) / 4 - (pts + ofs).unsqueeze(1)
+    dims = torch.stack((torch.full((N,), 3.9), -ob.kps_3d[:, -1, 1], torch.full((N,), 1.6)), dim=1)
+    depth, loc = dcd_b200.compute_pairs_kpts_depth(*cu(off, pts, ofs), pad_b.to(DEV), *cu(ob.kps_3d, ob.rot_y), ob.K.to(DEV),
+                                                   batch_idxs=ob.frame_id.to(DEV), dims=dims.to(DEV), return_locations=True)
+    # oracle: per image, with that image's matrix in float64 like the reference's calib.P
+    for f in range(len(counts)):
+        sel = (ob.frame_id == f).nonzero().squeeze(-1)
+        P = ob.K[sel[0]].double().numpy()
+        d_o, loc_o = O.frame_locations(off[sel], pts[sel], ofs[sel], pad_b[f:f + 1], ob.kps_3d[sel], ob.rot_y[sel], P, dims[sel])
+        assert rel_err(depth[sel.to(DEV)].cpu(), d_o) < 1e-5, f
+        assert bool(((loc[sel.to(DEV)].cpu() - loc_o).abs() <= 1e-4 + 1e-5 * loc_o.abs()).all()), f
+    # the solved depth tracks the generating depth, the location the generating translation
+    assert float(((depth.cpu() - ob.gt_depth).abs() / ob.gt_depth).median()) < 0.05
+
+
+def test_frame_epilogue_edge_cases():
+    e = dcd_b200.compute_pairs_kpts_depth(torch.empty((0, 73, 2), device=DEV), torch.empty((0, 2), device=DEV),
+                                          torch.empty((0, 2), device=DEV), torch.zeros(2, device=DEV),
+                                          torch.empty((0, 73, 3), device=DEV), torch.empty((0, 1), device=DEV),
+                                          np.array(synth.P2), return_locations=True)
+    assert e[0].shape == (0,) and e[1].shape == (0, 3)
+    with pytest.raises(RuntimeError):
+        dcd_b200.compute_pairs_kpts_depth(torch.zeros((2, 73, 2)), torch.zeros((2, 2)), torch.zeros((2, 2)), torch.zeros(2),
+                                          torch.zeros((2, 73, 3)), torch.zeros((2, 1)), np.array(synth.P2))     # CPU tensors
