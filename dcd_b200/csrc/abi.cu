@@ -17,6 +17,9 @@ int launch_gmw_weights_fwd(const float*, const float*, const float*, const float
                            float*, float*, float*, cudaStream_t);
 int launch_dgde_locate(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                        const float*, const float*, int64_t, int, float, float, int, float, float*, float*, cudaStream_t);
+int launch_dgde_depth_ensemble(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                               int64_t, float, float, float, float, float*, float*, float*, int64_t*, float*, cudaStream_t);
+int launch_gmw_ray_rescale(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
 size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
@@ -98,6 +101,29 @@ int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* 
     if (kpts_off ? (!kps3d || !rot) : !depth_in) return DCD_E_INVALID;
     return launch_dgde_locate(kpts_off, kps3d, rot, K, points, offsets, pad, dims, depth_in, N, kpts_off ? n : 2, lo, hi, flags,
                               down_ratio, depth_out, locations, (cudaStream_t)stream);
+}
+
+int dcd_dgde_depth_ensemble_fwd(const float* kp10, const float* dims, const float* K, const float* direct,
+                                const float* log_unc_direct, const float* log_unc_kp, const float* scores, int64_t N,
+                                float down_ratio, float eps, float lo, float hi, float* kp_depths, float* depth,
+                                float* depth_error, int64_t* argmax, float* scores_out, void* stream) {
+    if (N < 0) return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!kp10 || !dims || !K) return DCD_E_INVALID;
+    const bool ensemble = depth || depth_error || argmax || scores_out;
+    if (!ensemble && !kp_depths) return DCD_E_INVALID;
+    if (ensemble && (!log_unc_kp || (direct && !log_unc_direct))) return DCD_E_INVALID;
+    if (scores_out && !scores) return DCD_E_INVALID;
+    return launch_dgde_depth_ensemble(kp10, dims, K, direct, log_unc_direct, log_unc_kp, scores, N, down_ratio, eps, lo, hi,
+                                      kp_depths, depth, depth_error, argmax, scores_out, (cudaStream_t)stream);
+}
+
+int dcd_gmw_ray_rescale_fwd(const float* raw_location, const float* pred_depth, const float* dim, int64_t N,
+                            float* pred_location, void* stream) {
+    if (N < 0) return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!raw_location || !pred_depth || !dim || !pred_location) return DCD_E_INVALID;
+    return launch_gmw_ray_rescale(raw_location, pred_depth, dim, N, pred_location, (cudaStream_t)stream);
 }
 
 size_t dcd_gmw_param_count(int cin, int depth) { return (size_t)blob_size(cin, depth); }

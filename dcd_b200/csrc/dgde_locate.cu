@@ -108,3 +108,108 @@ int launch_dgde_locate(const float* kpts_off, const float* kps3d, const float* r
 }
 
 }  // namespace dcd
+
+// ---------------------------------------------------------------------------------------------
+// Rest of row N4: per-object depth ensemble of the detector head and the GMW-validation ray rescale.
+// One thread per object; every operation rounded like the reference's FP32 torch sequence.
+// ---------------------------------------------------------------------------------------------
+namespace dcd {
+namespace {
+
+// depth of one projected height: f_u * h3d / (relu(height) * down_ratio + eps)          anno_encoder.py:209-211
+__device__ __forceinline__ float height_depth(float fh, float height, float down_ratio, float eps) {
+    return __fdiv_rn(fh, __fadd_rn(__fmul_rn(fmaxf(height, 0.f), down_ratio), eps));
+}
+
+__global__ void __launch_bounds__(256)
+dgde_depth_ensemble_kernel(const float* __restrict__ kp10, const float* __restrict__ dims, const float* __restrict__ K,
+                           const float* __restrict__ direct, const float* __restrict__ log_unc_direct,
+                           const float* __restrict__ log_unc_kp, const float* __restrict__ scores, int64_t N, float down_ratio,
+                           float eps, float lo, float hi, float* __restrict__ kp_depths, float* __restrict__ depth,
+                           float* __restrict__ depth_error, int64_t* __restrict__ argmax, float* __restrict__ scores_out) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    const float* kp = kp10 + o * 20;
+    float v[10];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) v[t] = __ldg(kp + 2 * t + 1);
+    const float fh = __fmul_rn(__ldg(K + o * 12), __ldg(dims + o * 3 + 1));          // calib.f_u * pred_height_3D
+    // anno_encoder.py:199-201, 209-214, 221: centre line, corner pairs (0,4),(2,6) and (1,5),(3,7); mean of two; clamp
+    float d[4];
+    d[1] = height_depth(fh, __fsub_rn(v[8], v[9]), down_ratio, eps);
+    d[2] = __fmul_rn(__fadd_rn(height_depth(fh, __fsub_rn(v[0], v[4]), down_ratio, eps),
+                               height_depth(fh, __fsub_rn(v[2], v[6]), down_ratio, eps)), 0.5f);
+    d[3] = __fmul_rn(__fadd_rn(height_depth(fh, __fsub_rn(v[1], v[5]), down_ratio, eps),
+                               height_depth(fh, __fsub_rn(v[3], v[7]), down_ratio, eps)), 0.5f);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) d[j] = fminf(fmaxf(d[j], lo), hi);
+    if (kp_depths != nullptr) {
+        kp_depths[o * 3 + 0] = d[1]; kp_depths[o * 3 + 1] = d[2]; kp_depths[o * 3 + 2] = d[3];
+    }
+    if (depth == nullptr && depth_error == nullptr && argmax == nullptr && scores_out == nullptr) return;
+    // detector_infer.py:141,154,158-171: uncertainties = exp(channel); weights = (1/u) / sum(1/u)
+    const int first = direct != nullptr ? 0 : 1;
+    float u[4], w[4];
+    if (first == 0) {
+        d[0] = __ldg(direct + o);
+        u[0] = expf(__ldg(log_unc_direct + o));
+    }
+#pragma unroll
+    for (int j = 1; j < 4; ++j) u[j] = expf(__ldg(log_unc_kp + o * 3 + j - 1));
+    float wsum = 0.f;
+    int best = first;
+    for (int j = first; j < 4; ++j) {
+        w[j] = __fdiv_rn(1.f, u[j]);
+        wsum = __fadd_rn(wsum, w[j]);
+        if (w[j] > w[best]) best = j;                       // first maximum, like torch.argmax
+    }
+    float dsum = 0.f, esum = 0.f;
+    for (int j = first; j < 4; ++j) {
+        const float wn = __fdiv_rn(w[j], wsum);
+        dsum = __fadd_rn(dsum, __fmul_rn(d[j], wn));
+        esum = __fadd_rn(esum, __fmul_rn(wn, u[j]));
+    }
+    if (depth != nullptr) depth[o] = dsum;
+    if (depth_error != nullptr) depth_error[o] = esum;
+    if (argmax != nullptr) argmax[o] = best - first;
+    if (scores_out != nullptr) {                             // detector_infer.py:197-203
+        const float conf = __fsub_rn(1.f, fminf(fmaxf(esum, 0.01f), 1.f));
+        const float s = __fmul_rn(__ldg(scores + o), conf);
+        scores_out[o] = (esum != esum || s != s) ? 0.f : s;       // torch.clamp keeps NaN (fmaxf drops it): NaN -> 0
+    }
+}
+
+// GMW/main.py:542-547
+__global__ void __launch_bounds__(256)
+gmw_ray_rescale_kernel(const float* __restrict__ raw_location, const float* __restrict__ pred_depth, const float* __restrict__ dim,
+                       int64_t N, float* __restrict__ out) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    const float x = __ldg(raw_location + o * 3), y = __ldg(raw_location + o * 3 + 1), z = __ldg(raw_location + o * 3 + 2);
+    const float scale = __fdiv_rn(__ldg(pred_depth + o), z);
+    const float hh = __fmul_rn(__ldg(dim + o * 3), 0.5f);
+    out[o * 3 + 0] = __fmul_rn(scale, x);
+    out[o * 3 + 1] = __fadd_rn(__fmul_rn(scale, __fsub_rn(y, hh)), hh);
+    out[o * 3 + 2] = __fmul_rn(scale, z);
+}
+
+}  // namespace
+
+int launch_dgde_depth_ensemble(const float* kp10, const float* dims, const float* K, const float* direct, const float* lud,
+                               const float* luk, const float* scores, int64_t N, float down_ratio, float eps, float lo, float hi,
+                               float* kp_depths, float* depth, float* depth_error, int64_t* argmax, float* scores_out,
+                               cudaStream_t st) {
+    dgde_depth_ensemble_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(kp10, dims, K, direct, lud, luk, scores, N, down_ratio, eps,
+                                                                             lo, hi, kp_depths, depth, depth_error, argmax, scores_out);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+int launch_gmw_ray_rescale(const float* raw_location, const float* pred_depth, const float* dim, int64_t N, float* out,
+                           cudaStream_t st) {
+    gmw_ray_rescale_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(raw_location, pred_depth, dim, N, out);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

@@ -258,6 +258,69 @@ def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=Non
     return loc
 
 
+DEPTH_RANGE = (0.1, 100.0)   # MODEL.HEAD.DEPTH_RANGE (DGDE/config/defaults.py:196)
+KP_DEPTH_EPS = 1e-3          # Anno_Encoder.EPS (anno_encoder.py:17)
+
+
+def decode_depth_from_keypoints_batch(pred_keypoints, pred_dimensions, P, batch_idxs=None):
+    """Anno_Encoder.decode_depth_from_keypoints_batch (DGDE/model/anno_encoder.py:193-224) with the calibration as the
+    image's 3x4 matrix ([3,4]; [B,3,4] with batch_idxs; or per object [N,3,4]) -> [N,3] (centre, corner_02, corner_13)."""
+    require_cuda(pred_keypoints, pred_dimensions)
+    kp, dm = f32c(pred_keypoints).reshape(-1, 10, 2), f32c(pred_dimensions)
+    N, dev = kp.shape[0], kp.device
+    P = torch.as_tensor(P)
+    if P.dim() == 3 and batch_idxs is not None and P.shape[0] != N:
+        P = P.to(dev)[batch_idxs.to(dev).long()]
+    K = _calib_per_object(P, N, dev)
+    out = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    if N:
+        check(_lib.lib().dcd_dgde_depth_ensemble_fwd(ptr(kp), ptr(dm), ptr(K), 0, 0, 0, 0, N, DOWN_RATIO, KP_DEPTH_EPS,
+                                                     DEPTH_RANGE[0], DEPTH_RANGE[1], ptr(out), 0, 0, 0, 0, stream_ptr()),
+              "dcd_dgde_depth_ensemble_fwd")
+    return out
+
+
+def depth_ensemble(pred_keypoints, pred_dimensions, P, keypoint_log_uncertainty, direct_depths=None,
+                   direct_log_uncertainty=None, scores=None):
+    """Fused detector_infer.py:141-171,197-203: keypoint depths, uncertainties = exp(channels), inverse-uncertainty soft
+    ensemble -> dict(keypoint_depths [N,3], depth [N], depth_error [N], min_uncertainty [N] int64, scores [N,1] or None)."""
+    require_cuda(pred_keypoints, pred_dimensions, keypoint_log_uncertainty)
+    kp, dm = f32c(pred_keypoints).reshape(-1, 10, 2), f32c(pred_dimensions)
+    N, dev = kp.shape[0], kp.device
+    K = _calib_per_object(P, N, dev)
+    luk = f32c(keypoint_log_uncertainty).reshape(N, 3)
+    dd = f32c(direct_depths).reshape(-1) if direct_depths is not None else None
+    lud = f32c(direct_log_uncertainty).reshape(-1) if direct_log_uncertainty is not None else None
+    if (dd is None) != (lud is None):
+        raise RuntimeError("direct depth and its uncertainty channel go together")
+    sc = f32c(scores).reshape(-1) if scores is not None else None
+    kd = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((N,), dtype=torch.float32, device=dev)
+    err = torch.empty((N,), dtype=torch.float32, device=dev)
+    amax = torch.empty((N,), dtype=torch.int64, device=dev)
+    so = torch.empty((N,), dtype=torch.float32, device=dev) if sc is not None else None
+    if N:
+        check(_lib.lib().dcd_dgde_depth_ensemble_fwd(ptr(kp), ptr(dm), ptr(K), ptr(dd) if dd is not None else 0,
+                                                     ptr(lud) if lud is not None else 0, ptr(luk),
+                                                     ptr(sc) if sc is not None else 0, N, DOWN_RATIO, KP_DEPTH_EPS,
+                                                     DEPTH_RANGE[0], DEPTH_RANGE[1], ptr(kd), ptr(depth), ptr(err), ptr(amax),
+                                                     ptr(so) if so is not None else 0, stream_ptr()),
+              "dcd_dgde_depth_ensemble_fwd")
+    return {"keypoint_depths": kd, "depth": depth, "depth_error": err, "min_uncertainty": amax,
+            "scores": so.reshape(-1, 1) if so is not None else None}
+
+
+def ray_rescale(raw_location, pred_depth, dim):
+    """GMW/main.py:542-547: detector location [N,3] moved along its viewing ray to the GMW depth (dim [N,3] = (h,w,l))."""
+    require_cuda(raw_location, pred_depth, dim)
+    rl, pd, dm = f32c(raw_location), f32c(pred_depth).reshape(-1), f32c(dim)
+    out = torch.empty_like(rl)
+    if rl.shape[0]:
+        check(_lib.lib().dcd_gmw_ray_rescale_fwd(ptr(rl), ptr(pd), ptr(dm), rl.shape[0], ptr(out), stream_ptr()),
+              "dcd_gmw_ray_rescale_fwd")
+    return out
+
+
 def compute_z(kpts_2d, kpts_3d, pred_rot, num_k: int = K_SEL) -> Tuple[torch.Tensor, torch.Tensor]:
     """Drop-in for GMW/main.py:373-416: (Z_v_raw [b,E] clamped to [0.1,80], good_idx [b,1500] int64)."""
     require_cuda(kpts_2d, kpts_3d, pred_rot)

@@ -91,6 +91,24 @@ int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* 
                         const float* depth_in, int64_t N, int n, float lo, float hi, int flags, float down_ratio,
                         float* depth_out, float* locations, void* stream);
 
+/* Depth ensemble of the detector head (rest of row N4).  kp10 [N,10,2]: the regressed box keypoints (8 corners, bottom
+ * centre, top centre; feature-map units), dims [N,3] (l,h,w), K [N,3,4] (f_u = K[0][0]).
+ *   keypoint depths [N,3] = clamp(f_u * h / (relu(height) * down_ratio + eps), lo, hi) for the centre line and the two
+ *   diagonal corner pairs (mean of two each)                           DGDE/model/anno_encoder.py:193-224
+ *   uncertainties = exp(log_unc_*); weights = (1/u) / sum(1/u); depth = sum(w d); depth_error = sum(w u)
+ *   over {direct, 3 keypoint depths} (direct == NULL: the 3 keypoint depths)      detector_infer.py:141,154,158-171
+ *   scores_out = scores * (1 - clamp(depth_error, 0.01, 1)), NaN -> 0             detector_infer.py:197-203
+ * Every output may be NULL; argmax is torch.argmax of the weights (int64). */
+int dcd_dgde_depth_ensemble_fwd(const float* kp10, const float* dims, const float* K, const float* direct,
+                                const float* log_unc_direct, const float* log_unc_kp, const float* scores, int64_t N,
+                                float down_ratio, float eps, float lo, float hi, float* kp_depths, float* depth,
+                                float* depth_error, int64_t* argmax, float* scores_out, void* stream);
+
+/* GMW validation (GMW/main.py:542-547): move a detector location [N,3] along its viewing ray through the box centre to
+ * the GMW depth: scale = pred_depth / z; y -= h/2; loc *= scale; y += h/2  (dim [N,3] = (h,w,l) there). */
+int dcd_gmw_ray_rescale_fwd(const float* raw_location, const float* pred_depth, const float* dim, int64_t N,
+                            float* pred_location, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Edge solve, backward (the autograd of decode_pairs_kpts_depth, consumers detector_loss.py:188-214,
  * :388-396).  grad_depth is [N,k] when idx != NULL (gradient of the selected depths) or [N,E] when

@@ -343,6 +343,64 @@ def frame_locations(kpts_off, points, offsets, pad_size, kps_3d, rot_y, P, dims)
     return depth, loc
 
 
+def decode_depth_from_keypoints_batch(pred_keypoints, pred_dimensions, f_us, batch_idxs=None, down_ratio=DOWN_RATIO,
+                                      eps=1e-3, depth_range=(0.1, 100.0)):
+    """DGDE/model/anno_encoder.py:193-224: depth from the projected heights of the 3D box (centre line and the two
+    diagonal corner pairs).  pred_keypoints [N,10,2] (8 corners, bottom centre, top centre; feature-map units),
+    pred_dimensions [N,3] (l, h, w), f_us: calib.f_u of every image -> [N,3] (centre, corner_02, corner_13)."""
+    h3d = pred_dimensions[:, 1].clone()
+    if len(f_us) == 1:
+        batch_idxs = pred_dimensions.new_zeros(pred_dimensions.shape[0])
+    center_height = pred_keypoints[:, -2, 1] - pred_keypoints[:, -1, 1]
+    corner_02_height = pred_keypoints[:, [0, 2], 1] - pred_keypoints[:, [4, 6], 1]
+    corner_13_height = pred_keypoints[:, [1, 3], 1] - pred_keypoints[:, [5, 7], 1]
+    out = {"center": [], "corner_02": [], "corner_13": []}
+    for idx, gt_idx in enumerate(torch.unique(batch_idxs, sorted=True).tolist()):
+        f_u = float(f_us[idx])
+        sel = torch.nonzero(batch_idxs == gt_idx).squeeze(-1)
+        out["center"].append(f_u * h3d[sel] / (F.relu(center_height[sel]) * down_ratio + eps))
+        c02 = f_u * h3d[sel].unsqueeze(-1) / (F.relu(corner_02_height[sel]) * down_ratio + eps)
+        c13 = f_u * h3d[sel].unsqueeze(-1) / (F.relu(corner_13_height[sel]) * down_ratio + eps)
+        out["corner_02"].append(c02.mean(dim=1))
+        out["corner_13"].append(c13.mean(dim=1))
+    return torch.stack([torch.clamp(torch.cat(v), min=depth_range[0], max=depth_range[1]) for v in out.values()], dim=1)
+
+
+def depth_ensemble(direct_depths, keypoint_depths, direct_log_unc, keypoint_log_unc):
+    """DGDE/model/head/detector_infer.py:141,152,156-171: uncertainties = exp(channels); inverse-uncertainty weighted
+    soft ensemble of the direct depth and the three keypoint depths (or of the three alone when direct_depths is None).
+    -> (pred_depths [N], estimated_depth_error [N], argmax of the weights [N])."""
+    kp_unc = keypoint_log_unc.exp()
+    if direct_depths is not None:
+        depths = torch.cat((direct_depths.unsqueeze(1), keypoint_depths), dim=1)
+        unc = torch.cat((direct_log_unc.reshape(-1, 1).exp(), kp_unc), dim=1)
+    else:
+        depths, unc = keypoint_depths.clone(), kp_unc.clone()
+    w = 1 / unc
+    amax = w.argmax(dim=1)
+    w = w / w.sum(dim=1, keepdim=True)
+    return torch.sum(depths * w, dim=1), torch.sum(w * unc, dim=1), amax
+
+
+def uncertainty_scores(scores, estimated_depth_error):
+    """detector_infer.py:197-203: scores * (1 - clamp(error, 0.01, 1)), NaN -> 0.   scores [N,1] -> [N,1]."""
+    conf = 1 - torch.clamp(estimated_depth_error, min=0.01, max=1)
+    out = scores * conf.view(-1, 1)
+    out[torch.isnan(out)] = 0.0
+    return out
+
+
+def ray_rescale(raw_location, pred_depth, dim):
+    """GMW/main.py:542-547: move the detector's location along its viewing ray (through the box centre) to the GMW depth."""
+    raw_location = raw_location.clone()
+    scale = pred_depth / raw_location[:, 2]
+    h = dim[:, 0]
+    raw_location[:, 1] -= h / 2
+    pred_location = scale.unsqueeze(-1) * raw_location
+    pred_location[:, 1] += h / 2
+    return pred_location
+
+
 def random_state_dict(seed: int, depth: int = NET_DEPTH, dtype=torch.float32) -> Dict[str, torch.Tensor]:
     """Seeded weights with torch's Conv1d default init bounds and the reference's key names
     (used on the GPU box, where the reference module cannot be instantiated)."""

@@ -227,6 +227,62 @@ def locate_fixture(name, N, n, seed):
     print(name, "frame epilogue: depth err vs gt (median rel) %.4f" % float(((depth - ob.gt_depth).abs() / ob.gt_depth).median()))
 
 
+def ensemble_fixture(name, N, seed):
+    """Rest of row N4: decode_depth_from_keypoints_batch (anno_encoder.py:193-224, the unmodified method with the
+    reference's Calibration), the 4-depth uncertainty ensemble and the confidence (detector_infer.py:141-171,197-203,
+    executed line by line), and the GMW-val ray rescale (GMW/main.py:542-547)."""
+    enc = rl.load_dgde_anno_encoder()
+    enc.down_ratio, enc.EPS, enc.depth_range = O.DOWN_RATIO, 1e-3, [0.1, 100]
+    ob = synth.make_objects(N=N, n=73, seed=seed)
+    P = np.array(synth.P2, dtype=np.float64)
+    calib = load_reference_calibration(P)
+    kpts_off, points, offsets, pad, dims = frame_inputs(ob, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    kp10 = kpts_off[:, -10:, :].contiguous()                  # the box corners + bottom/top centres, feature-map units
+    kp10[::7, 1, 1] = kp10[::7, 5, 1] - 0.3                   # some inverted pairs: exercises relu + EPS and the clamp
+    direct = (ob.gt_depth * (1 + 0.05 * torch.randn(N, generator=g))).contiguous()
+    lu_d = (-1.5 + 0.5 * torch.randn((N, 1), generator=g)).contiguous()
+    lu_k = (-1.0 + 0.7 * torch.randn((N, 3), generator=g)).contiguous()
+    scores = torch.rand((N, 1), generator=g)
+    # --- reference
+    kd = enc.decode_depth_from_keypoints_batch(kp10, dims, [calib])                                  # :150
+    pred_direct_uncertainty = lu_d.exp()                                                             # :141
+    pred_keypoint_uncertainty = lu_k.exp()                                                           # :154
+    pred_combined_depths = torch.cat((direct.unsqueeze(1), kd), dim=1)                               # :159
+    pred_combined_uncertainty = torch.cat((pred_direct_uncertainty, pred_keypoint_uncertainty), dim=1)
+    depth_weights = 1 / pred_combined_uncertainty                                                    # :165
+    amax = depth_weights.argmax(dim=1)
+    depth_weights = depth_weights / depth_weights.sum(dim=1, keepdim=True)                           # :168
+    pred_depths = torch.sum(pred_combined_depths * depth_weights, dim=1)
+    estimated_depth_error = torch.sum(depth_weights * pred_combined_uncertainty, dim=1)              # :171
+    uncertainty_conf = 1 - torch.clamp(estimated_depth_error, min=0.01, max=1)                       # :198
+    sc = scores * uncertainty_conf.view(-1, 1)
+    sc[torch.isnan(sc)] = 0.0
+    # GMW validation: rescale a detector location to the GMW depth (main.py:542-547; dim = (h, w, l) there)
+    raw_location = torch.stack((0.3 * ob.gt_depth, torch.full((N,), 1.6), ob.gt_depth), dim=1)
+    dim_hwl = dims.roll(shifts=-1, dims=1)
+    pred_depth = direct
+    rl_in = raw_location.clone()
+    raw_depth = rl_in[:, 2]
+    scale = pred_depth / raw_depth
+    h = dim_hwl[:, 0]
+    rl_in[:, 1] -= h / 2
+    pred_location = scale.unsqueeze(-1) * rl_in
+    pred_location[:, 1] += h / 2
+    # --- oracle
+    kd_o = O.decode_depth_from_keypoints_batch(kp10, dims, [calib.f_u])
+    assert torch.equal(kd_o, kd), "oracle != reference (decode_depth_from_keypoints_batch)"
+    d_o, e_o, a_o = O.depth_ensemble(direct, kd, lu_d, lu_k)
+    assert torch.equal(d_o, pred_depths) and torch.equal(e_o, estimated_depth_error) and torch.equal(a_o, amax)
+    assert torch.equal(O.uncertainty_scores(scores, e_o), sc)
+    assert torch.equal(O.ray_rescale(raw_location, pred_depth, dim_hwl), pred_location)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kp10=npy(kp10), dims=npy(dims), P=P, direct=npy(direct),
+                        log_unc_direct=npy(lu_d), log_unc_kp=npy(lu_k), scores=npy(scores), keypoint_depths=npy(kd),
+                        depth=npy(pred_depths), depth_error=npy(estimated_depth_error), argmax=npy(amax), scores_out=npy(sc),
+                        raw_location=npy(raw_location), dim_hwl=npy(dim_hwl), pred_location=npy(pred_location))
+    print(name, "ensemble: clamped keypoint depths", int(((kd <= 0.1) | (kd >= 100)).sum()), "of", kd.numel())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -238,6 +294,7 @@ def main():
     gmw_fixture("gmw_n73_N4", N=4, seed=synth.BASE_SEED + 3, wseed=7)
     locate_fixture("locate_n73_N50", N=50, n=73, seed=synth.BASE_SEED + 20)   # one full frame
     locate_fixture("locate_n20_N7", N=7, n=20, seed=synth.BASE_SEED + 21)
+    ensemble_fixture("ensemble_N50", N=50, seed=synth.BASE_SEED + 22)
 
 
 if __name__ == "__main__":

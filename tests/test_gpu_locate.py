@@ -84,3 +84,34 @@ def test_frame_epilogue_edge_cases():
     with pytest.raises(RuntimeError):
         dcd_b200.compute_pairs_kpts_depth(torch.zeros((2, 73, 2)), torch.zeros((2, 2)), torch.zeros((2, 2)), torch.zeros(2),
                                           torch.zeros((2, 73, 3)), torch.zeros((2, 1)), np.array(synth.P2))     # CPU tensors
+
+
+def test_depth_ensemble_and_ray_rescale_vs_reference_fixture(golden):
+    """Rest of row N4 against outputs of the unmodified decode_depth_from_keypoints_batch (with the reference's
+    Calibration) and of the ensemble / confidence / ray-rescale lines executed verbatim (oracle/make_golden.py).
+    Tolerance 2e-6 relative: expf on the GPU and torch's CPU exp differ by an ulp."""
+    G = golden("ensemble_N50")
+    kp10, dims, direct, lud, luk, scores = cu(G["kp10"], G["dims"], G["direct"], G["log_unc_direct"], G["log_unc_kp"], G["scores"])
+    P = G["P"]
+    kd = dcd_b200.decode_depth_from_keypoints_batch(kp10, dims, P)
+    assert torch.equal(kd.cpu(), G["keypoint_depths"])            # no transcendental here: bit-exact
+    assert int(((kd <= 0.1) | (kd >= 100)).sum()) > 0              # the clamp and the relu + EPS path are exercised
+    out = dcd_b200.depth_ensemble(kp10, dims, P, luk, direct_depths=direct, direct_log_uncertainty=lud, scores=scores)
+    assert torch.equal(out["keypoint_depths"], kd)
+    assert rel_err(out["depth"].cpu(), G["depth"]) < 2e-6
+    assert rel_err(out["depth_error"].cpu(), G["depth_error"]) < 2e-6
+    assert torch.equal(out["min_uncertainty"].cpu(), G["argmax"])
+    assert rel_err(out["scores"].cpu(), G["scores_out"]) < 2e-6
+    # keypoint depths only (no direct depth head): oracle
+    o3 = dcd_b200.depth_ensemble(kp10, dims, P, luk)
+    d3, e3, a3 = O.depth_ensemble(None, G["keypoint_depths"], None, G["log_unc_kp"])
+    assert rel_err(o3["depth"].cpu(), d3) < 2e-6 and rel_err(o3["depth_error"].cpu(), e3) < 2e-6
+    assert torch.equal(o3["min_uncertainty"].cpu(), a3) and o3["scores"] is None
+    # NaN confidence -> score 0 (detector_infer.py:200-202)
+    bad = luk.clone()
+    bad[0, :] = float("nan")
+    assert float(dcd_b200.depth_ensemble(kp10, dims, P, bad, scores=scores)["scores"][0]) == 0.0
+    # GMW validation ray rescale
+    loc = dcd_b200.ray_rescale(*cu(G["raw_location"], G["direct"], G["dim_hwl"]))
+    assert torch.equal(loc.cpu(), G["pred_location"])
+    assert torch.equal(loc[:, 2].cpu(), (G["direct"] / G["raw_location"][:, 2]) * G["raw_location"][:, 2])
