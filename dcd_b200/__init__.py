@@ -9,9 +9,9 @@ weights (state_dict <-> parameter blob), synth (seeded KITTI-shaped objects), bu
 """
 from .ops import (GMW, K_SEL, compute_pairs_kpts_depth, compute_reg_loss, compute_z, decode_depth_from_keypoints_batch,
                   decode_location_flatten, decode_pairs_kpts_depth, depth_ensemble, edge_depth_mean, gmw_weighted_depth,
-                  ray_rescale)
+                  ray_rescale, select_point_of_interest)
 
 __all__ = ["GMW", "K_SEL", "compute_pairs_kpts_depth", "compute_reg_loss", "compute_z", "decode_depth_from_keypoints_batch",
            "decode_location_flatten", "decode_pairs_kpts_depth", "depth_ensemble", "edge_depth_mean", "gmw_weighted_depth",
-           "ray_rescale"]
+           "ray_rescale", "select_point_of_interest"]
 __version__ = "0.1.0"

@@ -20,6 +20,7 @@ int launch_dgde_locate(const float*, const float*, const float*, const float*, c
 int launch_dgde_depth_ensemble(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                                int64_t, float, float, float, float, float*, float*, float*, int64_t*, float*, cudaStream_t);
 int launch_gmw_ray_rescale(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
+int launch_poi_gather(const float*, const int64_t*, int64_t, int64_t, int, int64_t, float*, cudaStream_t);
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
 size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
@@ -116,6 +117,14 @@ int dcd_dgde_depth_ensemble_fwd(const float* kp10, const float* dims, const floa
     if (scores_out && !scores) return DCD_E_INVALID;
     return launch_dgde_depth_ensemble(kp10, dims, K, direct, log_unc_direct, log_unc_kp, scores, N, down_ratio, eps, lo, hi,
                                       kp_depths, depth, depth_error, argmax, scores_out, (cudaStream_t)stream);
+}
+
+int dcd_poi_gather_fwd(const float* feature_maps, const int64_t* index, int64_t B, int64_t K, int C, int64_t HW, float* out,
+                       void* stream) {
+    if (B < 0 || K < 0 || C < 1 || HW < 1) return DCD_E_INVALID;
+    if (B == 0 || K == 0) return DCD_OK;
+    if (!feature_maps || !index || !out) return DCD_E_INVALID;
+    return launch_poi_gather(feature_maps, index, B, K, C, HW, out, (cudaStream_t)stream);
 }
 
 int dcd_gmw_ray_rescale_fwd(const float* raw_location, const float* pred_depth, const float* dim, int64_t N,

@@ -213,3 +213,32 @@ int launch_gmw_ray_rescale(const float* raw_location, const float* pred_depth, c
 }
 
 }  // namespace dcd
+
+// ---------------------------------------------------------------------------------------------
+// Row N2, upstream gather: select_point_of_interest (DGDE/model/layers/utils.py:120-145) without the NCHW -> NHWC copy of
+// the whole regression map the reference makes to pick <= 50 points per image:  out[b, k, c] = feat[b, c, index[b, k]].
+// ---------------------------------------------------------------------------------------------
+namespace dcd {
+namespace {
+
+__global__ void __launch_bounds__(256)
+poi_gather_kernel(const float* __restrict__ feat, const int64_t* __restrict__ index, int64_t B, int64_t Kp, int C, int64_t HW,
+                  float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * Kp * C) return;
+    const int c = (int)(t % C);
+    const int64_t bk = t / C, b = bk / Kp;
+    const int64_t p = index[bk];
+    out[t] = (p >= 0 && p < HW) ? __ldg(feat + (b * C + c) * HW + p) : __int_as_float(0x7fc00000);   // out of range: NaN, no fault
+}
+
+}  // namespace
+
+int launch_poi_gather(const float* feat, const int64_t* index, int64_t B, int64_t Kp, int C, int64_t HW, float* out, cudaStream_t st) {
+    const int64_t total = B * Kp * C;
+    poi_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, index, B, Kp, C, HW, out);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

@@ -258,6 +258,25 @@ def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=Non
     return loc
 
 
+def select_point_of_interest(batch, index, feature_maps, validate: bool = False):
+    """Drop-in for DGDE/model/layers/utils.py:120-145: feature_maps [B,C,H,W], index [B,K] flattened positions (or
+    [B,K,2] (x, y) points) -> [B,K,C], reading only the selected values (no NHWC copy of the map).  An index outside the
+    map yields NaN; `validate=True` checks the range first (a host synchronisation) and raises like torch.gather."""
+    require_cuda(feature_maps, index)
+    fm = f32c(feature_maps)
+    B, C, H, W = fm.shape
+    if index.dim() == 3:
+        index = index[:, :, 1] * W + index[:, :, 0]
+    idx = index.reshape(batch, -1).long().contiguous()
+    if validate and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= H * W):
+        raise RuntimeError("index out of range")
+    out = torch.empty((B, idx.shape[1], C), dtype=torch.float32, device=fm.device)
+    if out.numel():
+        check(_lib.lib().dcd_poi_gather_fwd(ptr(fm), ptr(idx), B, idx.shape[1], C, H * W, ptr(out), stream_ptr()),
+              "dcd_poi_gather_fwd")
+    return out
+
+
 DEPTH_RANGE = (0.1, 100.0)   # MODEL.HEAD.DEPTH_RANGE (DGDE/config/defaults.py:196)
 KP_DEPTH_EPS = 1e-3          # Anno_Encoder.EPS (anno_encoder.py:17)
 

@@ -104,6 +104,13 @@ int dcd_dgde_depth_ensemble_fwd(const float* kp10, const float* dims, const floa
                                 float down_ratio, float eps, float lo, float hi, float* kp_depths, float* depth,
                                 float* depth_error, int64_t* argmax, float* scores_out, void* stream);
 
+/* Upstream gather (row N2): select_point_of_interest (DGDE/model/layers/utils.py:120-145).  feature_maps [B,C,H,W],
+ * index [B,K] int64 flattened positions y * W + x, out [B,K,C] = feature_maps[b, :, index[b,k]] (NaN for an index outside
+ * [0, H*W): no memory fault, no device-side assert).
+ * The reference permutes the whole map to NHWC first; this reads only the K*C selected values. */
+int dcd_poi_gather_fwd(const float* feature_maps, const int64_t* index, int64_t B, int64_t K, int C, int64_t HW,
+                       float* out, void* stream);
+
 /* GMW validation (GMW/main.py:542-547): move a detector location [N,3] along its viewing ray through the box centre to
  * the GMW depth: scale = pred_depth / z; y -= h/2; loc *= scale; y += h/2  (dim [N,3] = (h,w,l) there). */
 int dcd_gmw_ray_rescale_fwd(const float* raw_location, const float* pred_depth, const float* dim, int64_t N,

@@ -343,6 +343,18 @@ def frame_locations(kpts_off, points, offsets, pad_size, kps_3d, rot_y, P, dims)
     return depth, loc
 
 
+def select_point_of_interest(batch, index, feature_maps):
+    """DGDE/model/layers/utils.py:120-145: regression channels at the points of interest, [B,C,H,W] -> [B,K,C]."""
+    w = feature_maps.shape[3]
+    if index.dim() == 3:
+        index = index[:, :, 1] * w + index[:, :, 0]
+    index = index.view(batch, -1)
+    fm = feature_maps.permute(0, 2, 3, 1).contiguous()
+    channel = fm.shape[-1]
+    fm = fm.view(batch, -1, channel)
+    return fm.gather(1, index.unsqueeze(-1).repeat(1, 1, channel).long())
+
+
 def decode_depth_from_keypoints_batch(pred_keypoints, pred_dimensions, f_us, batch_idxs=None, down_ratio=DOWN_RATIO,
                                       eps=1e-3, depth_range=(0.1, 100.0)):
     """DGDE/model/anno_encoder.py:193-224: depth from the projected heights of the 3D box (centre line and the two

@@ -283,6 +283,24 @@ def ensemble_fixture(name, N, seed):
     print(name, "ensemble: clamped keypoint depths", int(((kd <= 0.1) | (kd >= 100)).sum()), "of", kd.numel())
 
 
+def poi_fixture(name, seed):
+    """Row N2 gather: the unmodified select_point_of_interest (DGDE/model/layers/utils.py:120-145)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_layers_utils", os.path.join(rl.REFERENCE_ROOT, "DGDE", "model", "layers", "utils.py"))
+    lu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lu)
+    g = torch.Generator().manual_seed(seed)
+    B, C, H, W, K = 2, 37, 24, 80, 50
+    fm = torch.randn((B, C, H, W), generator=g)
+    idx = torch.randint(0, H * W, (B, K), generator=g)
+    ref = lu.select_point_of_interest(B, idx, fm)
+    pts = torch.stack((idx % W, idx // W), dim=-1)
+    assert torch.equal(lu.select_point_of_interest(B, pts, fm), ref)
+    assert torch.equal(O.select_point_of_interest(B, idx, fm), ref) and torch.equal(O.select_point_of_interest(B, pts, fm), ref)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), feature_maps=npy(fm), index=npy(idx), pois=npy(ref))
+    print(name, "poi gather", tuple(ref.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -295,6 +313,7 @@ def main():
     locate_fixture("locate_n73_N50", N=50, n=73, seed=synth.BASE_SEED + 20)   # one full frame
     locate_fixture("locate_n20_N7", N=7, n=20, seed=synth.BASE_SEED + 21)
     ensemble_fixture("ensemble_N50", N=50, seed=synth.BASE_SEED + 22)
+    poi_fixture("poi_gather", seed=synth.BASE_SEED + 23)
 
 
 if __name__ == "__main__":

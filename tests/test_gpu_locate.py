@@ -115,3 +115,22 @@ def test_depth_ensemble_and_ray_rescale_vs_reference_fixture(golden):
     loc = dcd_b200.ray_rescale(*cu(G["raw_location"], G["direct"], G["dim_hwl"]))
     assert torch.equal(loc.cpu(), G["pred_location"])
     assert torch.equal(loc[:, 2].cpu(), (G["direct"] / G["raw_location"][:, 2]) * G["raw_location"][:, 2])
+
+
+def test_poi_gather_vs_reference_fixture(golden):
+    """Row N2 gather: bit-exact against the unmodified select_point_of_interest, index and point forms, plus a
+    detector-sized map (the reference would copy all of it to NHWC)."""
+    G = golden("poi_gather")
+    fm, idx = cu(G["feature_maps"], G["index"])
+    out = dcd_b200.select_point_of_interest(fm.shape[0], idx, fm)
+    assert torch.equal(out.cpu(), G["pois"])
+    W = fm.shape[3]
+    pts = torch.stack((idx % W, idx // W), dim=-1)
+    assert torch.equal(dcd_b200.select_point_of_interest(fm.shape[0], pts, fm).cpu(), G["pois"])
+    big = torch.randn((2, 440, 96, 320), device=DEV)
+    bi = torch.randint(0, 96 * 320, (2, 50), device=DEV)
+    assert torch.equal(dcd_b200.select_point_of_interest(2, bi, big), O.select_point_of_interest(2, bi, big))
+    with pytest.raises(RuntimeError):
+        dcd_b200.select_point_of_interest(2, bi + 96 * 320, big, validate=True)
+    assert bool(torch.isnan(dcd_b200.select_point_of_interest(2, bi + 96 * 320, big)).all())     # no fault without it
+    assert dcd_b200.select_point_of_interest(2, bi[:, :0], big).shape == (2, 0, 440)
