@@ -301,6 +301,54 @@ def poi_fixture(name, seed):
     print(name, "poi gather", tuple(ref.shape))
 
 
+def wire_fixture(seed):
+    """Row N3: small gen_data_train.json / gen_data_infer.json in the reference writers' layout (detector_loss.py:148-173 +
+    trainer.py:208-215; inference.py:59-84, json.dump(..., indent=4)) and what the unmodified reader
+    (GMW/utilities/dataset_utilities.py:11-56) makes of them."""
+    import importlib.util
+    import json
+    import types
+    spec = importlib.util.spec_from_file_location(
+        "ref_dataset_utilities", os.path.join(rl.REFERENCE_ROOT, "GMW", "utilities", "dataset_utilities.py"))
+    du = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(du)
+    # training file: per iteration a list over the batch's objects (two iterations of 3 and 2 objects)
+    train = {k: [] for k in ("kpts_2d", "kpts_3d", "img_idx", "pred_rot", "gt_location", "pred_location")}
+    for it, nobj in enumerate((3, 2)):
+        ob = synth.make_objects(N=nobj, n=73, seed=seed + it)
+        train["kpts_2d"].append(ob.kps_norm.numpy().tolist())
+        train["kpts_3d"].append(ob.kps_3d.numpy().tolist())
+        train["img_idx"].append(["%06d" % (10 * it + j) for j in range(nobj)])
+        train["pred_rot"].append(ob.rot_y.reshape(-1).numpy().tolist())
+        loc = torch.stack((0.3 * ob.gt_depth, torch.full((nobj,), 1.6), ob.gt_depth), dim=1)
+        train["gt_location"].append(loc.numpy().tolist())
+        train["pred_location"].append((loc * 1.01).numpy().tolist())
+    # inference file: image id -> list of detections (83 keypoints regressed, GMW keeps the first 73)
+    infer = {}
+    for img, nobj in (("000007", 2), ("000123", 3)):
+        ob = synth.make_objects(N=nobj, n=83, seed=seed + int(img))
+        infer[img] = []
+        for j in range(nobj):
+            infer[img].append({"kpts_2d": ob.kps_norm[j].numpy().tolist(), "kpts_3d": ob.kps_3d[j].numpy().tolist(),
+                               "pred_rot": ob.rot_y[j].numpy().tolist(), "box": [10.0, 20.0, 110.0, 90.0],
+                               "dim": [1.5, 1.6, 3.9], "pred_location": [0.3 * float(ob.gt_depth[j]), 1.6, float(ob.gt_depth[j])],
+                               "score": [0.9], "cat": "Car"})
+    tp, ip = os.path.join(OUT, "gen_data_train_small.json"), os.path.join(OUT, "gen_data_infer_small.json")
+    json.dump(train, open(tp, "w"), indent=4)
+    json.dump(infer, open(ip, "w"), indent=4)
+    args = types.SimpleNamespace(train_data_path=tp, val_data_path=ip)
+    ref_t = du.load_data(args, "train")
+    ref_v = du.load_data(args, "valid")
+    from dcd_b200 import wire
+    for ref, split, path in ((ref_t, "train", tp), (ref_v, "valid", ip)):
+        mine = wire.load_reference_json(path, split)
+        for k, v in ref.items():
+            assert mine[k].dtype == v.dtype and mine[k].shape == v.shape and np.array_equal(mine[k], v), (split, k)
+    np.savez_compressed(os.path.join(OUT, "wire_reference_load_data.npz"),
+                        **{"train_" + k: v for k, v in ref_t.items()}, **{"valid_" + k: v for k, v in ref_v.items()})
+    print("wire fixture:", {k: v.shape for k, v in ref_v.items()}, os.path.getsize(tp), os.path.getsize(ip))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -314,6 +362,7 @@ def main():
     locate_fixture("locate_n20_N7", N=7, n=20, seed=synth.BASE_SEED + 21)
     ensemble_fixture("ensemble_N50", N=50, seed=synth.BASE_SEED + 22)
     poi_fixture("poi_gather", seed=synth.BASE_SEED + 23)
+    wire_fixture(seed=synth.BASE_SEED + 24)
 
 
 if __name__ == "__main__":
