@@ -1,5 +1,6 @@
-// GMW edge-feature MLP forward, inference form: ONE kernel for all 37 layers of a net, the object's
-// activations never leave the chip (sm_100a: tcgen05 + TMEM, persistent co-resident CTA groups).
+// GMW edge-feature MLP forward, inference form: ONE kernel for the whole net (conv_in + 12 blocks; each block's
+// preconv and conv1 folded into one layer: 1 + 24 layers instead of 1 + 36), the object's activations never leave
+// the chip (sm_100a: tcgen05 + TMEM, persistent co-resident CTA groups).
 //
 // The layer-wise kernels (gmw_mlp_tc.cu) are bound by HBM: every context norm needs the statistics of the
 // whole object, so each of the 24 normalised layers writes its output and reads it back (198 MB / object).
@@ -19,8 +20,8 @@
 // Warp roles: 12 converter warps (thread = channel; accumulators -> context norm / ReLU / residual -> FP16
 // hi/lo operand; statistics of the layer output), 4 service warps (weight image -> tensor memory; the first one
 // issues the MMAs from an elected lane).  Hand-offs are mbarriers; there is no CTA-wide barrier per sub-tile.
-// Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, FP32 statistics);
-// only the order in which the statistics partials are merged differs.
+// Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, FP32 statistics) up to
+// the folded layer (Wf = W1.Wp formed in FP64, rounded once) and the order in which the statistics partials are merged.
 // HBM traffic: keypoints in, final features out (2.75 MB / object instead of 198 MB).
 #include "gmw_tc_common.cuh"
 
