@@ -290,3 +290,31 @@ def test_gmw_batch_properties_medium():
     assert bool(torch.isfinite(a).all()) and float(a.min()) >= 0.1 and float(a.max()) <= 80.0
     # depth estimate tracks the generating depth on geometry-consistent inputs even with random weights
     assert float(((a.cpu() - ob.gt_depth).abs() / ob.gt_depth).median()) < 0.1
+
+
+def test_inference_entry_is_cuda_graph_capturable():
+    """Boundary contract: the C entry points neither synchronise nor allocate, so the fused inference path —
+    including the cooperative launch of the on-chip MLP kernel — can be captured in a CUDA graph and replayed."""
+    ob = synth.make_objects(N=24, n=73, seed=321)
+    model = make_model(O.random_state_dict(5))
+    k2, k3, rot = cu(ob.kps_norm, ob.kps_3d, ob.rot_y)
+    eager = dcd_b200.gmw_weighted_depth(k2, k3, rot, model)             # also warms the lazy per-device setup
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        dcd_b200.gmw_weighted_depth(k2, k3, rot, model)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = dcd_b200.gmw_weighted_depth(k2, k3, rot, model)
+    k2b = k2.clone()
+    k2.copy_(cu(synth.make_objects(N=24, n=73, seed=322).kps_norm)[0])  # new inputs in the captured buffers
+    g.replay()
+    torch.cuda.synchronize()
+    fresh = dcd_b200.gmw_weighted_depth(k2, k3, rot, model)
+    assert torch.equal(out, fresh) and not torch.equal(out, eager)
+    k2.copy_(k2b)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
