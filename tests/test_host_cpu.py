@@ -70,6 +70,17 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.dcd_edge_select_fwd(8, 8, 8, 8, 0, 5, 8, 1500, 2.0, 80.0, 3, 8, 8, 0, 0, 0) == -1   # k > E (28 edges)
     assert lib.dcd_gmw_aggregate_fwd(8, 8, 8, 4, 100, 200, 0, 8, 0, 0) == -1               # k > E
     assert lib.dcd_gmw_weights_fwd(8, 8, 16, 16, 4, 73, 12, 0, 8, 0, 0, 256, 16, 0) == -2  # workspace too small
+    # frame epilogue entries
+    assert lib.dcd_dgde_locate_fwd(8, 8, 8, 0, 8, 8, 8, 0, 0, 5, 73, 2.0, 80.0, 3, 4.0, 8, 8, 0) == -1       # K is required
+    assert lib.dcd_dgde_locate_fwd(8, 8, 8, 8, 8, 8, 8, 0, 0, 5, 73, 2.0, 80.0, 3, 4.0, 0, 0, 0) == -1       # no output
+    assert lib.dcd_dgde_locate_fwd(0, 0, 0, 8, 8, 8, 8, 0, 0, 5, 73, 2.0, 80.0, 3, 4.0, 0, 8, 0) == -1       # no solve: depth_in
+    assert lib.dcd_dgde_locate_fwd(8, 8, 8, 8, 8, 8, 8, 0, 0, 5, 300, 2.0, 80.0, 3, 4.0, 8, 8, 0) == -1      # n > 256
+    assert lib.dcd_dgde_locate_fwd(8, 8, 8, 8, 8, 8, 8, 0, 0, 0, 73, 2.0, 80.0, 3, 4.0, 8, 8, 0) == 0        # N = 0
+    assert lib.dcd_dgde_depth_ensemble_fwd(8, 8, 8, 8, 0, 8, 0, 5, 4.0, 1e-3, 0.1, 100.0, 8, 8, 8, 0, 0, 0) == -1   # direct without its uncertainty
+    assert lib.dcd_dgde_depth_ensemble_fwd(8, 8, 8, 0, 0, 8, 0, 5, 4.0, 1e-3, 0.1, 100.0, 0, 0, 0, 0, 8, 0) == -1   # scores_out without scores
+    assert lib.dcd_dgde_depth_ensemble_fwd(8, 8, 8, 0, 0, 0, 0, 5, 4.0, 1e-3, 0.1, 100.0, 0, 0, 0, 0, 0, 0) == -1   # nothing to compute
+    assert lib.dcd_poi_gather_fwd(8, 8, 2, 50, 0, 100, 8, 0) == -1 and lib.dcd_poi_gather_fwd(8, 8, 0, 50, 4, 100, 8, 0) == 0
+    assert lib.dcd_gmw_ray_rescale_fwd(8, 8, 0, 5, 8, 0) == -1 and lib.dcd_gmw_ray_rescale_fwd(8, 8, 8, 0, 8, 0) == 0
 
 
 def test_ops_reject_cpu_tensors():
