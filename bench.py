@@ -394,7 +394,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": N * 4,
                     "api": "dcd_b200.gmw_weighted_depth on pinned host tensors"},
             "gpu_launches": timed_launches,
-            "roofline": {"kernel": "mlp_fused_kernel (edge-feature MLP, all 37 layers of a net in one cluster-of-8 launch: activations "
+            "roofline": {"kernel": "mlp_fused_kernel (edge-feature MLP, the whole net of an object in one launch by a group of 8 co-resident CTAs: activations "
                                    "stay in shared/tensor memory; preconv.conv1 folded: 24 GEMM layers x 2 nets on tcgen05, FP16x3 split, FP32 accumulate "
                                    "in TMEM)",
                          "bound": "tensor",

@@ -47,7 +47,7 @@ __device__ int g_trace_n[2];
 #endif
 namespace {
 
-constexpr int FCS = 8;              // CTAs per cluster = edge slices per object
+constexpr int FCS = 8;              // CTAs per group = edge slices per object
 constexpr int FCONV_WARPS = 12;     // converter warps: 4 TMEM lane quarters x 3 units (16 edges) of a 48-edge sub-tile
 constexpr int FCONV_THREADS = 32 * FCONV_WARPS;
 constexpr int FTHREADS = FCONV_THREADS + 128;   // + 4 service warps: weight loads (all 4), MMA issue (the first)
