@@ -365,6 +365,8 @@ def main():
         if world > 1:
             ddist.allreduce_gradients(train_model)
     ms_train = time_kernel(train_step, reps=5)
+    # correspondence branch, forward: E x E distances + Sinkhorn for the same 8 objects, P not materialised
+    ms_cls = time_kernel(lambda: train_model.edge_transport(t_k2, t_k3, materialise=False), reps=3)
 
     # ---- reduce over ranks (max time) and report
     times = torch.tensor([ms, e2e_ms, mlp_ms], dtype=torch.float64, device=dev)
@@ -432,6 +434,9 @@ def main():
                 "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": tb * world / (ms_train * 1e-3),
                                       "what": "configs[2]: compute_z + edge MLP fwd + softmax aggregate + L1 loss + full backward (all GEMMs on "
                                               "tcgen05) for 8 objects per GPU%s; optimizer step excluded" % (" + gradient all-reduce" if world > 1 else "")},
+                "gmw_cls_forward_b8": {"ms": ms_cls, "objects_per_s": tb / (ms_cls * 1e-3),
+                                       "what": "edge MLP + E x E feature distances + Sinkhorn (lambda 10, <= 100 iterations, "
+                                               "GMW/model/model.py:170-192) -> sum P, trace P for 8 objects; forward only"},
                 "fp32_peak_tflops": fp32_peak,
             },
             "clocks": clocks,

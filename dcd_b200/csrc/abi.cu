@@ -21,6 +21,9 @@ int launch_dgde_depth_ensemble(const float*, const float*, const float*, const f
                                int64_t, float, float, float, float, float*, float*, float*, int64_t*, float*, cudaStream_t);
 int launch_gmw_ray_rescale(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_poi_gather(const float*, const int64_t*, int64_t, int64_t, int, int64_t, float*, cudaStream_t);
+size_t gmw_transport_workspace_bytes(int64_t N, int E);
+int launch_gmw_transport_fwd(const float*, const float*, int64_t, int, float, float, int, float*, float*, float*, float*, void*,
+                             cudaStream_t);
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
 size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
@@ -133,6 +136,22 @@ int dcd_gmw_ray_rescale_fwd(const float* raw_location, const float* pred_depth, 
     if (N == 0) return DCD_OK;
     if (!raw_location || !pred_depth || !dim || !pred_location) return DCD_E_INVALID;
     return launch_gmw_ray_rescale(raw_location, pred_depth, dim, N, pred_location, (cudaStream_t)stream);
+}
+
+size_t dcd_gmw_transport_workspace_bytes(int64_t N, int n) {
+    if (N <= 0 || bad_n(n)) return 0;
+    return gmw_transport_workspace_bytes(N, (int)num_edges(n));
+}
+
+int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int n, float lambda, float tolerance,
+                          int max_iterations, float* P, float* u, float* v, float* sums, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (N < 0 || bad_n(n) || max_iterations < 0 || !(lambda > 0.f)) return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!feat4 || !feat6 || (!P && !u && !v && !sums)) return DCD_E_INVALID;
+    if (misaligned(workspace, 256) || workspace_bytes < dcd_gmw_transport_workspace_bytes(N, n)) return DCD_E_WORKSPACE;
+    return launch_gmw_transport_fwd(feat4, feat6, N, (int)num_edges(n), lambda, tolerance, max_iterations, P, u, v, sums, workspace,
+                                    (cudaStream_t)stream);
 }
 
 size_t dcd_gmw_param_count(int cin, int depth) { return (size_t)blob_size(cin, depth); }

@@ -1,0 +1,250 @@
+// Correspondence branch of GMW, forward: pairwise feature distances + entropy-regularised transport.
+//   f4n, f6n  = L2-normalised final edge features of the two nets                      GMW/model/model.py:176-177
+//   M[i][j]   = sqrt(max((|c_j|^2 - 2 a_i.c_j) + |a_i|^2, 1e-30))                      model.py:17-36 (pairwiseL2Dist)
+//   K         = exp(-lambda * min(M, 5));  u = r;  repeat <= max_iter:                  GMW/lib/optimal_transport.py:52-72
+//                   stop when |u - u_prev| <= tol everywhere (whole batch);  u = r / (K (c / (K^T u)))
+//   v = c / (K^T u);  P = (u * K) * v^T          with r = 1/E, c = 1/E                  model.py:186-191
+// Both training and validation loops consume P only through correspondenceLoss(P, eye) = sum(P) - 2 trace(P)
+// (GMW/main.py:456-457,526-527, lib/losses.py:22-26,115-119), so the kernels also return those two sums per object and
+// P itself is optional.  The backward (implicit differentiation with an E x E Cholesky, optimal_transport.py:75-128) is
+// not built.
+//
+// K is E x E FP32 (27.6 MB per object at n = 73) in the caller's workspace; every Sinkhorn iteration streams it twice
+// (column pass K^T u with the rows split over 16 partial sums, row pass K w with a warp per row), deterministic: no
+// atomics on floating-point data.  The convergence test is a device flag, later iterations become no-ops.
+#include "gmw_mlp.cuh"
+
+namespace dcd {
+namespace {
+
+constexpr int TP_CHUNKS = 16;       // row chunks of the column pass
+
+// per-edge norms of the final features and the squared norms of the normalised vectors (model.py:176-177, :27-28)
+__global__ void __launch_bounds__(256) transport_norm_kernel(const float* __restrict__ feat4, const float* __restrict__ feat6,
+                                                             int64_t N, int E, float* __restrict__ nrm /* [N][4][E] */) {
+    const int64_t obj = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= E) return;
+    const float* X4 = feat4 + obj * (int64_t)CH * E + e;
+    const float* X6 = feat6 + obj * (int64_t)CH * E + e;
+    float n4 = 0.f, n6 = 0.f;
+    for (int c = 0; c < CH; ++c) {
+        const float x4 = X4[(int64_t)c * E], x6 = X6[(int64_t)c * E];
+        n4 = fmaf(x4, x4, n4);
+        n6 = fmaf(x6, x6, n6);
+    }
+    n4 = fmaxf(sqrtf(n4), 1e-12f);
+    n6 = fmaxf(sqrtf(n6), 1e-12f);
+    float a2 = 0.f, c2 = 0.f;
+    for (int c = 0; c < CH; ++c) {
+        const float av = __fdiv_rn(X4[(int64_t)c * E], n4), cv = __fdiv_rn(X6[(int64_t)c * E], n6);
+        a2 = fmaf(av, av, a2);
+        c2 = fmaf(cv, cv, c2);
+    }
+    float* o = nrm + obj * 4 * (int64_t)E;
+    o[e] = n4; o[E + e] = n6; o[2 * (int64_t)E + e] = a2; o[3 * (int64_t)E + e] = c2;
+}
+
+// K tile: 64 x 64 outputs, 128-deep dot products of the normalised features, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256) transport_k_kernel(const float* __restrict__ feat4, const float* __restrict__ feat6,
+                                                          const float* __restrict__ nrm, int E, float lambda, float max_distance,
+                                                          float* __restrict__ Kmat) {
+    extern __shared__ float sm[];                           // A[128][64], B[128][64]
+    float* As = sm;
+    float* Bs = sm + CH * 64;
+    const int64_t obj = blockIdx.z;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const float* nr = nrm + obj * 4 * (int64_t)E;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < CH * 64; idx += 256) {
+        const int c = idx >> 6, t = idx & 63;
+        const int i = i0 + t, j = j0 + t;
+        As[idx] = i < E ? __fdiv_rn(feat4[(obj * CH + c) * (int64_t)E + i], nr[i]) : 0.f;
+        Bs[idx] = j < E ? __fdiv_rn(feat6[(obj * CH + c) * (int64_t)E + j], nr[E + j]) : 0.f;
+    }
+    __syncthreads();
+    const int ti = (tid >> 4) * 4, tj = (tid & 15) * 4;
+    float acc[4][4] = {};
+#pragma unroll 4
+    for (int c = 0; c < CH; ++c) {
+        const float4 a = *reinterpret_cast<const float4*>(As + c * 64 + ti);
+        const float4 b = *reinterpret_cast<const float4*>(Bs + c * 64 + tj);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int i = i0 + ti + p;
+        if (i >= E) continue;
+        const float a2 = nr[2 * (int64_t)E + i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + tj + q;
+            if (j >= E) continue;
+            const float c2 = nr[3 * (int64_t)E + j];
+            const float m = sqrtf(fmaxf(__fadd_rn(__fadd_rn(c2, -2.f * acc[p][q]), a2), 1e-30f));
+            Kmat[(obj * E + i) * (int64_t)E + j] = expf(-lambda * fminf(m, max_distance));
+        }
+    }
+}
+
+// column pass: partial[obj][chunk][j] = sum over the chunk's rows i of K[i][j] * u[i]
+__global__ void __launch_bounds__(256) transport_col_kernel(const float* __restrict__ Kmat, const float* __restrict__ u, int E,
+                                                            const int* __restrict__ stop, float* __restrict__ partial) {
+    if (stop != nullptr && *stop) return;
+    const int64_t obj = blockIdx.z;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int rows = (E + TP_CHUNKS - 1) / TP_CHUNKS;
+    const int ib = blockIdx.y * rows, ie = min(E, ib + rows);
+    if (j >= E) return;
+    const float* Kp = Kmat + obj * (int64_t)E * E + j;
+    const float* up = u + obj * (int64_t)E;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = ib; i < ie; ++i) acc = fmaf(Kp[(int64_t)i * E], up[i], acc);
+    partial[(obj * TP_CHUNKS + blockIdx.y) * (int64_t)E + j] = acc;
+}
+
+// w[j] = c / (K^T u)[j]   (partials summed in chunk order)
+__global__ void __launch_bounds__(256) transport_w_kernel(const float* __restrict__ partial, int E, float cval, const int* __restrict__ stop,
+                                                          float* __restrict__ w) {
+    if (stop != nullptr && *stop) return;
+    const int64_t obj = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= E) return;
+    float t = 0.f;
+    for (int k = 0; k < TP_CHUNKS; ++k) t += partial[(obj * TP_CHUNKS + k) * (int64_t)E + j];
+    w[obj * (int64_t)E + j] = __fdiv_rn(cval, t);
+}
+
+// row pass (a warp per row): u[i] = r / (K w)[i]; raises *changed when |u - u_old| > tol anywhere
+__global__ void __launch_bounds__(256) transport_row_kernel(const float* __restrict__ Kmat, const float* __restrict__ w, int E, float rval,
+                                                            float tol, const int* __restrict__ stop, float* __restrict__ u,
+                                                            int* __restrict__ changed) {
+    if (stop != nullptr && *stop) return;
+    const int64_t obj = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= E) return;
+    const float* Kp = Kmat + (obj * E + i) * (int64_t)E;
+    const float* wp = w + obj * (int64_t)E;
+    float acc = 0.f;
+    for (int j = lane; j < E; j += 32) acc = fmaf(Kp[j], wp[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float un = __fdiv_rn(rval, acc);
+        const float uo = u[obj * (int64_t)E + i];
+        u[obj * (int64_t)E + i] = un;
+        if (!(fabsf(un - uo) <= tol)) atomicOr(changed, 1);
+    }
+}
+
+// stop[k] = !changed[k]: the iteration after a converged one (and all later ones) does nothing.  Also seeds u = r.
+__global__ void transport_flag_kernel(int* __restrict__ flags, int it) {
+    // flags[0] = stop, flags[1] = changed of the iteration that just ran
+    if (it > 0 && flags[1] == 0) flags[0] = 1;
+    flags[1] = 0;
+}
+__global__ void __launch_bounds__(256) transport_fill_kernel(float* __restrict__ p, int64_t n, float v) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t < n) p[t] = v;
+}
+
+// P = (u * K) * v^T (optional), sums[obj] = (sum P, trace P)   — a warp per row, per-row partials reduced by a second kernel
+__global__ void __launch_bounds__(256) transport_p_kernel(const float* __restrict__ Kmat, const float* __restrict__ u,
+                                                          const float* __restrict__ v, int E, float* __restrict__ P,
+                                                          float* __restrict__ rowsum /* [N][2][E] */) {
+    const int64_t obj = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= E) return;
+    const float* Kp = Kmat + (obj * E + i) * (int64_t)E;
+    const float* vp = v + obj * (int64_t)E;
+    const float ui = u[obj * (int64_t)E + i];
+    float acc = 0.f, diag = 0.f;
+    for (int j = lane; j < E; j += 32) {
+        const float p = __fmul_rn(__fmul_rn(ui, Kp[j]), vp[j]);
+        if (P != nullptr) P[(obj * E + i) * (int64_t)E + j] = p;
+        acc += p;
+        if (j == i) diag = p;
+    }
+    acc = warp_sum(acc);
+    diag = warp_sum(diag);
+    if (lane == 0) {
+        rowsum[(obj * 2) * (int64_t)E + i] = acc;
+        rowsum[(obj * 2 + 1) * (int64_t)E + i] = diag;
+    }
+}
+__global__ void __launch_bounds__(256) transport_sum_kernel(const float* __restrict__ rowsum, int E, float* __restrict__ sums) {
+    __shared__ float red[2][8];
+    const int64_t obj = blockIdx.x;
+    float a = 0.f, d = 0.f;
+    for (int i = threadIdx.x; i < E; i += 256) {
+        a += rowsum[(obj * 2) * (int64_t)E + i];
+        d += rowsum[(obj * 2 + 1) * (int64_t)E + i];
+    }
+    a = warp_sum(a);
+    d = warp_sum(d);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = d; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.f; d = 0.f;
+        for (int k = 0; k < 8; ++k) { a += red[0][k]; d += red[1][k]; }
+        sums[obj * 2] = a;
+        sums[obj * 2 + 1] = d;
+    }
+}
+
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+// workspace: K [N][E][E] | norms [N][4][E] | u, w (v) [N][E] each | partial [N][16][E] | row sums [N][2][E] | flags
+size_t gmw_transport_workspace_bytes(int64_t N, int E) {
+    const size_t e = (size_t)E;
+    return al((size_t)N * e * e * 4) + al((size_t)N * 4 * e * 4) + 2 * al((size_t)N * e * 4) + al((size_t)N * TP_CHUNKS * e * 4) +
+           al((size_t)N * 2 * e * 4) + 256;
+}
+
+int launch_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int E, float lambda, float tol, int max_iter,
+                             float* P, float* u_out, float* v_out, float* sums, void* workspace, cudaStream_t st) {
+    const size_t e = (size_t)E;
+    unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+    float* Kmat = reinterpret_cast<float*>(p); p += al((size_t)N * e * e * 4);
+    float* nrm = reinterpret_cast<float*>(p); p += al((size_t)N * 4 * e * 4);
+    float* u = reinterpret_cast<float*>(p); p += al((size_t)N * e * 4);
+    float* w = reinterpret_cast<float*>(p); p += al((size_t)N * e * 4);
+    float* partial = reinterpret_cast<float*>(p); p += al((size_t)N * TP_CHUNKS * e * 4);
+    float* rowsum = reinterpret_cast<float*>(p); p += al((size_t)N * 2 * e * 4);
+    int* flags = reinterpret_cast<int*>(p);
+    const unsigned eb = (unsigned)((E + 255) / 256), rb = (unsigned)((E + 7) / 8), tb = (unsigned)((E + 63) / 64);
+    const float rc = 1.0f / (float)E;                        // r = c = 1 / E (model.py:186-190)
+    cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
+    transport_norm_kernel<<<dim3(eb, (unsigned)N), 256, 0, st>>>(feat4, feat6, N, E, nrm);
+    constexpr int kSmem = 2 * CH * 64 * sizeof(float);
+    cudaFuncSetAttribute(transport_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    transport_k_kernel<<<dim3(tb, tb, (unsigned)N), 256, kSmem, st>>>(feat4, feat6, nrm, E, lambda, 5.0f, Kmat);
+    transport_fill_kernel<<<(unsigned)((N * e + 255) / 256), 256, 0, st>>>(u, (int64_t)(N * e), rc);
+    DCD_CHECK_LAUNCH();
+    // optimal_transport.py:63-69: the test at the top of iteration 0 compares u = r with u_prev = 1 (never close), so
+    // iteration 0 always runs; iteration k > 0 runs iff iteration k-1 changed u by more than tol somewhere in the batch
+    for (int it = 0; it < max_iter; ++it) {
+        transport_flag_kernel<<<1, 1, 0, st>>>(flags, it);
+        transport_col_kernel<<<dim3(eb, TP_CHUNKS, (unsigned)N), 256, 0, st>>>(Kmat, u, E, flags, partial);
+        transport_w_kernel<<<dim3(eb, (unsigned)N), 256, 0, st>>>(partial, E, rc, flags, w);
+        transport_row_kernel<<<dim3(rb, (unsigned)N), 256, 0, st>>>(Kmat, w, E, rc, tol, flags, u, flags + 1);
+    }
+    DCD_CHECK_LAUNCH();
+    // v = c / (K^T u), P = (u * K) * v^T
+    transport_col_kernel<<<dim3(eb, TP_CHUNKS, (unsigned)N), 256, 0, st>>>(Kmat, u, E, nullptr, partial);
+    transport_w_kernel<<<dim3(eb, (unsigned)N), 256, 0, st>>>(partial, E, rc, nullptr, w);
+    transport_p_kernel<<<dim3(rb, (unsigned)N), 256, 0, st>>>(Kmat, u, w, E, P, rowsum);
+    if (sums != nullptr) transport_sum_kernel<<<(unsigned)N, 256, 0, st>>>(rowsum, E, sums);
+    if (u_out != nullptr) cudaMemcpyAsync(u_out, u, (size_t)N * e * 4, cudaMemcpyDeviceToDevice, st);
+    if (v_out != nullptr) cudaMemcpyAsync(v_out, w, (size_t)N * e * 4, cudaMemcpyDeviceToDevice, st);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
+
+}  // namespace dcd

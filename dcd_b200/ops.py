@@ -439,7 +439,9 @@ class GMW(nn.Module):
 
     forward(kpts_2d, kpts_3d, pred_rot, args) -> (reg_weights [b,E], edge_P); `pred_rot` and `args`
     are ignored as in the reference.  edge_P (the Sinkhorn correspondence matrix
-    of the classification branch) is not computed and returned as None.
+    of the classification branch) is returned as None by forward(); its forward
+    (no gradient) is available through `edge_transport`, and forward() returns it too when the module
+    attribute `with_edge_P` is set and gradients are disabled (validation loop of GMW/main.py:524-527).
     Parameters live in two flat blobs; `load_state_dict`/`state_dict` of the *reference* format
     are available through `load_reference_state_dict` / `reference_state_dict`.
     """
@@ -449,6 +451,7 @@ class GMW(nn.Module):
         self.depth = depth
         self.params4 = nn.Parameter(torch.zeros(blob_size(4, depth)))
         self.params6 = nn.Parameter(torch.zeros(blob_size(6, depth)))
+        self.with_edge_P = False
 
     def load_reference_state_dict(self, sd: Dict[str, torch.Tensor]) -> "GMW":
         sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}   # main.py:286-289
@@ -469,12 +472,45 @@ class GMW(nn.Module):
             out.update({k: v.clone() for k, v in unpack_blob(p.grad, name, cin, self.depth).items()})
         return out
 
+    SINKHORN_LAMBDA, SINKHORN_TOLERANCE, SINKHORN_ITERATIONS = 10.0, 1e-9, 100     # GMW/model/model.py:117-119
+
+    @torch.no_grad()
+    def edge_transport(self, kpts_2d, kpts_3d, materialise: bool = True):
+        """Correspondence branch, forward only (GMW/model/model.py:170-192): returns
+        (reg_weights [b,E], edge_P [b,E,E] or None, cls_terms [b,2] = (sum P, trace P)).
+        correspondenceLoss(edge_P, eye) of GMW/main.py:456-457 is `(cls_terms[:, 0] - 2 * cls_terms[:, 1]).mean()`;
+        with materialise=False the 4 E^2 bytes per object of edge_P are never written.  No gradient."""
+        require_cuda(kpts_2d, kpts_3d, self.params4)
+        k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
+        N, n = k2.shape[0], k2.shape[1]
+        E = _num_edges(n)
+        dev = k2.device
+        L = _lib.lib()
+        reg_w = torch.empty((N, E), dtype=torch.float32, device=dev)
+        P = torch.empty((N, E, E), dtype=torch.float32, device=dev) if materialise else None
+        sums = torch.empty((N, 2), dtype=torch.float32, device=dev)
+        if N:
+            f4 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
+            f6 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
+            ws = _alloc_bytes(L.dcd_gmw_workspace_bytes(N, n, self.depth, 0), dev)
+            check(L.dcd_gmw_weights_fwd(ptr(k2), ptr(k3), ptr(self.params4), ptr(self.params6), N, n, self.depth, 0,
+                                        ptr(reg_w), ptr(f4), ptr(f6), ptr(ws), ws.numel() * 4, stream_ptr()), "dcd_gmw_weights_fwd")
+            del ws
+            tws = _alloc_bytes(L.dcd_gmw_transport_workspace_bytes(N, n), dev)
+            check(L.dcd_gmw_transport_fwd(ptr(f4), ptr(f6), N, n, self.SINKHORN_LAMBDA, self.SINKHORN_TOLERANCE,
+                                          self.SINKHORN_ITERATIONS, ptr(P) if P is not None else 0, 0, 0, ptr(sums),
+                                          ptr(tws), tws.numel() * 4, stream_ptr()), "dcd_gmw_transport_fwd")
+        return reg_w, P, sums
+
     def forward(self, kpts_2d, kpts_3d, pred_rot=None, args=None):
         require_cuda(kpts_2d, kpts_3d, self.params4)
         k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
         if k2.dim() != 3 or k2.shape[-1] != 2 or tuple(k3.shape) != (k2.shape[0], k2.shape[1], 3):
             raise ValueError("kpts_2d must be [b,n,2] and kpts_3d [b,n,3]")
         need_grad = torch.is_grad_enabled() and (self.params4.requires_grad or self.params6.requires_grad)
+        if self.with_edge_P and not need_grad:
+            reg_w, P, _ = self.edge_transport(k2, k3)
+            return reg_w, P
         reg_w = _GmwWeights.apply(k2, k3, self.params4, self.params6, self.depth, need_grad)
         if _CHECK_FINITE and not bool(torch.isfinite(reg_w).all()):
             # the tensor-core path carries activations as FP16 hi+lo pairs: |activation| must stay below 65504

@@ -154,6 +154,17 @@ int dcd_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* p
                         int64_t N, int n, int depth, int save, float* reg_weights,
                         float* feat4, float* feat6, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Correspondence branch of GMW, forward only: from the final features feat4 / feat6 [N,128,E] of
+ * dcd_gmw_weights_fwd:  M = pairwiseL2Dist(normalise(f4), normalise(f6)) (GMW/model/model.py:17-36,176-180),
+ * P = Sinkhorn(M; r = c = 1/E, lambda, tolerance, max_iterations) (GMW/lib/optimal_transport.py:52-72, model.py:186-191).
+ * Outputs (each may be NULL): P [N,E,E], u / v [N,E] (P = diag(u) K diag(v), K = exp(-lambda min(M,5))),
+ * sums [N,2] = (sum P, trace P) — correspondenceLoss(P, eye) = mean over objects of sum - 2 trace (lib/losses.py:22-26,
+ * 115-119; GMW/main.py:456-457,526-527).  The workspace holds K (4 E^2 bytes per object).  No backward. */
+size_t dcd_gmw_transport_workspace_bytes(int64_t N, int n);
+int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int n, float lambda, float tolerance,
+                          int max_iterations, float* P, float* u, float* v, float* sums, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Backward of dcd_gmw_weights_fwd w.r.t. the parameters (autograd of GMW/main.py:465 on the reg path).
  * workspace: the one filled by the forward call with save=1 (same N, n, depth).  grad_reg_weights [N,E].
  * grad_params4 / grad_params6: same layout as the parameter blobs, OVERWRITTEN with the sum over the N

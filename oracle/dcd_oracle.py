@@ -251,6 +251,48 @@ def gmw_reg_weights(kpts_2d, kpts_3d, sd, depth: int = NET_DEPTH, full_matrix: b
     return w
 
 
+def pairwise_l2_dist(x1, x2):
+    """GMW/model/model.py:17-36."""
+    x1_norm2 = x1.pow(2).sum(dim=-1, keepdim=True)
+    x2_norm2 = x2.pow(2).sum(dim=-1, keepdim=True)
+    return torch.baddbmm(x2_norm2.transpose(-2, -1), x1, x2.transpose(-2, -1), alpha=-2).add_(x1_norm2).clamp_min_(1e-30).sqrt_()
+
+
+def sinkhorn(M, r, c, lmbda=10.0, tolerance=1e-9, max_iterations=100, max_distance=5.0):
+    """GMW/lib/optimal_transport.py:52-72 (RegularisedTransportFn.sinkhorn) with tensor r, c."""
+    K = (-lmbda * M.clamp_max(max_distance)).exp()
+    r = r.unsqueeze(-1)
+    c = c.unsqueeze(-1)
+    u = r.clone()
+    u_prev = torch.ones_like(u)
+    for _ in range(max_iterations):
+        if torch.all(torch.isclose(u, u_prev, atol=tolerance, rtol=0.0)):
+            break
+        u_prev = u
+        u = r / K.matmul(c / K.transpose(-2, -1).matmul(u))
+    v = c / K.transpose(-2, -1).matmul(u)
+    return (u * K) * v.transpose(-2, -1)
+
+
+def gmw_edge_transport(kpts_2d, kpts_3d, sd, depth: int = NET_DEPTH):
+    """GMW/model/model.py:170-192: (edge_P [b,E,E], reg_weights [b,E])."""
+    f4 = edge_net(edge_expand(kpts_2d).transpose(-2, -1), sd, "FeatureExtractor4d", depth).transpose(-2, -1)
+    f6 = edge_net(edge_expand(kpts_3d).transpose(-2, -1), sd, "FeatureExtractor6d", depth).transpose(-2, -1)
+    f4 = F.normalize(f4, p=2, dim=-1)
+    f6 = F.normalize(f6, p=2, dim=-1)
+    M = pairwise_l2_dist(f4, f6)
+    diag = 1. / M.diagonal(offset=0, dim1=-2, dim2=-1)
+    b, m, n = M.size()
+    r = M.new_ones((b, m)) / m
+    c = M.new_ones((b, n)) / n
+    return sinkhorn(M, r, c), diag
+
+
+def correspondence_loss(P, C):
+    """GMW/lib/losses.py:22-26,115-119."""
+    return ((1.0 - 2.0 * C) * P).sum(dim=(-2, -1)).mean()
+
+
 def compute_reg_loss(pre_depths, edge_weight, gt_depth, good_idx):
     """GMW/main.py:364-371."""
     z = pre_depths.gather(-1, good_idx)

@@ -349,6 +349,35 @@ def wire_fixture(seed):
     print("wire fixture:", {k: v.shape for k, v in ref_v.items()}, os.path.getsize(tp), os.path.getsize(ip))
 
 
+def transport_fixture(name, N, seed, wseed):
+    """Row N1 forward: the unmodified GMW.forward (E x E pairwiseL2Dist + RegularisedTransport Sinkhorn, GMW/model/model.py:170-207,
+    GMW/lib/optimal_transport.py:52-72) on N objects.  edge_P is 27.6 MB per object, so the fixture keeps what the loops use
+    (sum P, trace P, correspondenceLoss against eye: main.py:456-457) plus its diagonal, marginals and three full rows."""
+    main, _ = rl.load_gmw()
+    ob = synth.make_objects(N=N, n=73, seed=seed)
+    sd = O.random_state_dict(wseed)
+    model = rl.new_gmw_model(0)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        t0 = time.time()
+        w_ref, P_ref = model(ob.kps_norm, ob.kps_3d, ob.rot_y, None)
+        t_ref = time.time() - t0
+        P_o, diag_o = O.gmw_edge_transport(ob.kps_norm, ob.kps_3d, sd)
+    assert torch.equal(P_o, P_ref) and torch.equal(diag_o, w_ref), "oracle != reference (edge transport)"
+    eye = torch.eye(P_ref.shape[1]).expand_as(P_ref)
+    from lib.losses import correspondenceLoss
+    cls_ref = correspondenceLoss(P_ref, eye)
+    assert torch.equal(O.correspondence_loss(P_ref, eye), cls_ref)
+    rows = [0, 1313, 2627]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kps_norm=npy(ob.kps_norm), kps_3d=npy(ob.kps_3d),
+                        weight_seed=np.array(wseed), reg_weights=npy(w_ref), P_sum=npy(P_ref.sum((-2, -1))),
+                        P_trace=npy(P_ref.diagonal(dim1=-2, dim2=-1).sum(-1)), P_diag=npy(P_ref.diagonal(dim1=-2, dim2=-1)),
+                        P_rowsum=npy(P_ref.sum(-1)), P_colsum=npy(P_ref.sum(-2)), P_rows=npy(P_ref[:, rows, :]),
+                        rows=np.array(rows), cls_loss=npy(cls_ref))
+    print(name, "reference forward incl. Sinkhorn %.1f s, cls_loss %.6f, sum P" % (t_ref, float(cls_ref)), P_ref.sum((-2, -1)).tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -363,6 +392,7 @@ def main():
     ensemble_fixture("ensemble_N50", N=50, seed=synth.BASE_SEED + 22)
     poi_fixture("poi_gather", seed=synth.BASE_SEED + 23)
     wire_fixture(seed=synth.BASE_SEED + 24)
+    transport_fixture("transport_n73_N2", N=2, seed=synth.BASE_SEED + 25, wseed=7)
 
 
 if __name__ == "__main__":

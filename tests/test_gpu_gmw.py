@@ -318,3 +318,45 @@ def test_inference_entry_is_cuda_graph_capturable():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_edge_transport_forward_vs_reference_fixture(golden):
+    """Row N1, forward: pairwise distances + Sinkhorn on the GPU against the unmodified reference (fixture holds
+    sum P, trace P, the diagonal, the marginals and three full rows of the 2628 x 2628 plan of two objects)."""
+    G = golden("transport_n73_N2")
+    model = make_model(O.random_state_dict(int(G["weight_seed"])))
+    k2, k3 = cu(G["kps_norm"], G["kps_3d"])
+    w, P, sums = model.edge_transport(k2, k3)
+    E = 2628
+    assert P.shape == (2, E, E) and sums.shape == (2, 2)
+    assert rel_err(w.cpu(), G["reg_weights"]) < 1e-4
+    assert rel_err(sums[:, 0].cpu(), G["P_sum"]) < 1e-5 and rel_err(sums[:, 1].cpu(), G["P_trace"]) < 1e-4
+    assert rel_err(P.diagonal(dim1=-2, dim2=-1).cpu(), G["P_diag"]) < 2e-4
+    assert rel_err(P[:, G["rows"].tolist(), :].cpu(), G["P_rows"]) < 2e-4
+    assert rel_err(P.sum(-1).cpu(), G["P_rowsum"]) < 1e-4 and rel_err(P.sum(-2).cpu(), G["P_colsum"]) < 1e-4
+    cls = float((sums[:, 0] - 2 * sums[:, 1]).mean())                      # correspondenceLoss(P, eye), main.py:456-457
+    assert abs(cls - float(G["cls_loss"])) < 1e-6
+    assert torch.allclose(sums[:, 0], P.sum((-2, -1)), rtol=1e-5, atol=0) and torch.allclose(sums[:, 1], P.diagonal(dim1=-2, dim2=-1).sum(-1), rtol=1e-5, atol=0)
+    # sums only (P never written), and the module's forward in validation mode
+    w2, none, sums2 = model.edge_transport(k2, k3, materialise=False)
+    assert none is None and torch.equal(sums2, sums) and torch.equal(w2, w)
+    model.with_edge_P = True
+    with torch.no_grad():
+        w3, P3 = model(k2, k3, None, None)
+    assert torch.equal(P3, P) and torch.equal(w3, w)
+    w4, P4 = model(k2, k3, None, None)                                      # gradients enabled: regression branch only
+    assert P4 is None and w4.requires_grad
+
+
+def test_edge_transport_small_shapes_vs_oracle():
+    """n != 73 (E not a multiple of the tiles), shallow nets; oracle evaluated on the GPU."""
+    for n, depth, N in ((9, 1, 3), (20, 2, 2)):
+        ob = synth.make_objects(N=N, n=n, seed=300 + n)
+        sd = O.random_state_dict(n, depth=depth)
+        model = make_model(sd, depth)
+        k2, k3 = cu(ob.kps_norm, ob.kps_3d)
+        w, P, sums = model.edge_transport(k2, k3)
+        with torch.no_grad():
+            P_o, w_o = O.gmw_edge_transport(k2, k3, {k: v.to(DEV) for k, v in sd.items()}, depth)
+        assert rel_err(w, w_o) < 1e-4 and rel_err(P, P_o) < 5e-4, (n, depth)
+        assert rel_err(sums[:, 0], P_o.sum((-2, -1))) < 1e-5
