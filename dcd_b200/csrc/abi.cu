@@ -149,6 +149,7 @@ int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int
     if (N < 0 || bad_n(n) || max_iterations < 0 || !(lambda > 0.f)) return DCD_E_INVALID;
     if (N == 0) return DCD_OK;
     if (!feat4 || !feat6 || (!P && !u && !v && !sums)) return DCD_E_INVALID;
+    if (N > 65535) return DCD_E_UNSUPPORTED;                  // objects map to gridDim.y / .z; K alone is 27.6 MB per object
     if (misaligned(workspace, 256) || workspace_bytes < dcd_gmw_transport_workspace_bytes(N, n)) return DCD_E_WORKSPACE;
     return launch_gmw_transport_fwd(feat4, feat6, N, (int)num_edges(n), lambda, tolerance, max_iterations, P, u, v, sums, workspace,
                                     (cudaStream_t)stream);

@@ -159,7 +159,7 @@ int dcd_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* p
  * P = Sinkhorn(M; r = c = 1/E, lambda, tolerance, max_iterations) (GMW/lib/optimal_transport.py:52-72, model.py:186-191).
  * Outputs (each may be NULL): P [N,E,E], u / v [N,E] (P = diag(u) K diag(v), K = exp(-lambda min(M,5))),
  * sums [N,2] = (sum P, trace P) — correspondenceLoss(P, eye) = mean over objects of sum - 2 trace (lib/losses.py:22-26,
- * 115-119; GMW/main.py:456-457,526-527).  The workspace holds K (4 E^2 bytes per object).  No backward. */
+ * 115-119; GMW/main.py:456-457,526-527).  The workspace holds K (4 E^2 bytes per object); N <= 65535.  No backward. */
 size_t dcd_gmw_transport_workspace_bytes(int64_t N, int n);
 int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int n, float lambda, float tolerance,
                           int max_iterations, float* P, float* u, float* v, float* sums, void* workspace,
