@@ -130,8 +130,30 @@ __global__ void __launch_bounds__(256) transport_row_kernel(const float* __restr
     if (i >= E) return;
     const float* Kp = Kmat + (obj * E + i) * (int64_t)E;
     const float* wp = w + obj * (int64_t)E;
+    // rows are 16-byte aligned when E % 4 == 0 (E = 2628): 512 bytes per warp and load, four loads in flight
     float acc = 0.f;
-    for (int j = lane; j < E; j += 32) acc = fmaf(Kp[j], wp[j], acc);
+    if ((E & 3) == 0) {
+        const float4* K4 = reinterpret_cast<const float4*>(Kp);
+        const float4* w4 = reinterpret_cast<const float4*>(wp);
+        const int E4 = E >> 2;
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        int j = lane;
+        for (; j + 96 < E4; j += 128) {
+            float4 k[4], x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { k[q] = __ldcs(K4 + j + 32 * q); x[q] = w4[j + 32 * q]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                a4[q] = fmaf(k[q].w, x[q].w, fmaf(k[q].z, x[q].z, fmaf(k[q].y, x[q].y, fmaf(k[q].x, x[q].x, a4[q]))));
+        }
+        for (; j < E4; j += 32) {
+            const float4 k = __ldcs(K4 + j), x = w4[j];
+            a4[0] = fmaf(k.w, x.w, fmaf(k.z, x.z, fmaf(k.y, x.y, fmaf(k.x, x.x, a4[0]))));
+        }
+        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    } else {
+        for (int j = lane; j < E; j += 32) acc = fmaf(Kp[j], wp[j], acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
         const float un = __fdiv_rn(rval, acc);
