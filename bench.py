@@ -351,6 +351,21 @@ def main():
                                                              ptr(pad_o), ptr(dims_o), 0, N, N_KPTS, 2.0, 80.0, 3, 4.0, ptr(mean),
                                                              ptr(loc_o), st), "locate"))
 
+    # one frame of the detector head (50 detections) through the public API: POI gather on a [1,440,96,320] regression map,
+    # fused keypoints -> edge solve -> location, depth ensemble: latency, launch overheads included
+    fr = 50
+    fmap = torch.randn((1, 440, 96, 320), device=dev)
+    fidx = torch.randint(0, 96 * 320, (1, fr), device=dev)
+    P_np = ob.K[0].double().numpy()
+    lu_k = torch.zeros((fr, 3), device=dev)
+
+    def frame_epilogue():
+        dcd_b200.select_point_of_interest(1, fidx, fmap)
+        d, _ = dcd_b200.compute_pairs_kpts_depth(off_o[:fr], pts_o[:fr], ofs_o[:fr], pad_o[:1], d_k3[:fr], d_rot[:fr], P_np,
+                                                 dims=dims_o[:fr], return_locations=True)
+        dcd_b200.depth_ensemble(off_o[:fr, -10:], dims_o[:fr], P_np, lu_k, direct_depths=d, direct_log_uncertainty=lu_k[:, 0])
+    ms_frame = time_kernel(frame_epilogue, reps=20)
+
     # ---- GMW training step, batch 8 per GPU (BASELINE configs[2]): compute_z + forward (saved) + loss + backward
     tb = 8
     t_k2, t_k3, t_rot, t_gt = d_k2[:tb].contiguous(), d_k3[:tb].contiguous(), d_rot[:tb].reshape(-1, 1).contiguous(), ob.gt_depth[:tb].to(dev)
@@ -430,6 +445,9 @@ def main():
                                         "hbm_gbs": (B_SOLVE + 52) * N / (ms_loc * 1e-3) / 1e9,
                                         "what": "keypoint offsets -> image keypoints -> edge solve + mean -> 3D location "
                                                 "(detector_infer.py:215-227,186-188), one launch"},
+                "dgde_frame_latency": {"us": ms_frame * 1e3, "objects": fr,
+                                       "what": "one frame, 50 detections, python API: select_point_of_interest + compute_pairs_kpts_depth "
+                                               "(with locations) + depth_ensemble; three launches, host overheads included"},
                 "edge_select_top1500": {"objects_per_s": sel_n / (ms_sel * 1e-3), "ms": ms_sel, "objects": sel_n},
                 "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": tb * world / (ms_train * 1e-3),
                                       "what": "configs[2]: compute_z + edge MLP fwd + softmax aggregate + L1 loss + full backward (all GEMMs on "
