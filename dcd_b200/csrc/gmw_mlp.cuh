@@ -56,6 +56,10 @@ __host__ __device__ inline float2* stat_ptr(float* ws, const WsLayout& L, int ne
     return reinterpret_cast<float2*>(ws + L.stats_off) + (((int64_t)net * L.depth + blk) * 2 + which) * L.stat;
 }
 
+// Folded layer of a block: there is no non-linearity between preconv and conv1 (ops.py:125-131), so the layer-wise
+// kernels run  Wf = W1 . Wp,  bf = W1 . bp + b1  as ONE GEMM.  Fold area per (net, block): Wf^T [in][out], then bf [128].
+constexpr int64_t FOLD_STRIDE = (int64_t)CH * CH + CH;
+
 // arguments shared by the forward kernels
 struct MlpArgs {
     const float* kpts2d;
@@ -63,6 +67,7 @@ struct MlpArgs {
     const float* params[2];
     float* ws;
     WsLayout L;
+    const float* fold;     // [2][depth] folded layers (FOLD_STRIDE floats each), written by tc_fold_prep_kernel
 };
 
 }  // namespace dcd

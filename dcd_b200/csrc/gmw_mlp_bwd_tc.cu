@@ -29,6 +29,8 @@ struct BwdTcArgs {
     float* ws;              // forward workspace (save = 1)
     WsLayout L;
     const float2* scales;   // per-matrix (scale, 1/scale) written by the forward
+    const float* fold;      // folded layers Wf^T, bf per (net, block) written by the forward (FOLD_STRIDE floats each)
+    float* dwf;             // [2][128*128] gradient of the folded layer, blob layout [in][out]
     float* G;               // [2][N][128][EP] gradient w.r.t. the current block output
     float* D1;              // [2][N][128][EP] gradient w.r.t. yhat1
     float* DP;              // [2][N][128][EP] gradient w.r.t. the preconv output
@@ -38,9 +40,13 @@ struct BwdTcArgs {
     float* gmax;            // [2][3*depth + 1] running |gradient| maxima (float bits, >= 0)
 };
 
+size_t tc_fold_offset_bytes(int depth);
+
 namespace {
 
-enum { MODE_R2 = 0, MODE_R3A = 1, MODE_R3B = 2 };
+// R2: dy2, dW2, dyhat1.  R3F: dy1 (context-norm backward), dWf, dx + residual for the folded preconv.conv1 layer.
+// (R3A / R3B are the same two steps for the unfolded pair of layers; kept for reference, not launched.)
+enum { MODE_R2 = 0, MODE_R3A = 1, MODE_R3B = 2, MODE_R3F = 3 };
 constexpr int BT_THREADS = 512;
 constexpr uint32_t TMB_W_HI = 0, TMB_W_LO = 64, TMB_DW = 128, TMB_D = 256;
 constexpr size_t SMB_A1 = 0;                                       // gradient image  {hi, lo} 64 KB (also the output staging)
@@ -212,7 +218,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMB_BAR + 16);
 
     // ---- setup: barrier, tensor memory, W^T resident as the A operand of the data-gradient GEMM
-    const int which = (MODE == MODE_R2) ? 2 : (MODE == MODE_R3A ? 1 : 0);
+    const int which = (MODE == MODE_R2) ? 2 : ((MODE == MODE_R3A || MODE == MODE_R3F) ? 1 : 0);
+    constexpr bool kResidual = MODE == MODE_R3B || MODE == MODE_R3F;      // output = dx of the block: add the skip gradient
+    constexpr bool kCnBackward = MODE == MODE_R3A || MODE == MODE_R3F;    // gradient image = context-norm backward of y1
     const int mat = (net * L.depth + blk) * 3 + which;
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -227,13 +235,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
     const float2 wsc = __ldg(a.scales + mat);
     if (warp < 8)
-        load_weight_row_to_tmem_T(prm + blob_w(cin, blk, which), wsc.x, ch, tmem_base + lane_off + TMB_W_HI,
-                                  tmem_base + lane_off + TMB_W_LO, cq & 1);
+        load_weight_row_to_tmem_T(MODE == MODE_R3F ? a.fold + ((int64_t)net * L.depth + blk) * FOLD_STRIDE : prm + blob_w(cin, blk, which),
+                                  wsc.x, ch, tmem_base + lane_off + TMB_W_HI, tmem_base + lane_off + TMB_W_LO, cq & 1);
     // scale of the gradient image from the running maximum of what feeds it
-    const float gin = a.gmax[gmax_slot(L.depth, net, blk, MODE)];
+    const float gin = a.gmax[gmax_slot(L.depth, net, blk, MODE == MODE_R3F ? 1 : MODE)];
     const float gs = pow2_scale(gin, MODE == MODE_R3B ? 10 : 4);     // R2/R3A: |dy| <= ~1700 x the tracked maximum
     const float un_d = wsc.y / gs;                                    // data-gradient accumulator -> FP32
-    float* gout = a.gmax + (MODE == MODE_R3B ? (blk > 0 ? gmax_slot(L.depth, net, blk - 1, 0) : gmax_slot(L.depth, net, L.depth, 0))
+    float* gout = a.gmax + (kResidual ? (blk > 0 ? gmax_slot(L.depth, net, blk - 1, 0) : gmax_slot(L.depth, net, L.depth, 0))
                                              : gmax_slot(L.depth, net, blk, MODE + 1));
     tc_fence_before();
     __syncthreads();
@@ -275,10 +283,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                 S1p = act_ptr(a.ws, L, net, blk, SLOT_Y2) + obj_off;
                 S2p = a.G + gobj;
                 S3p = act_ptr(a.ws, L, net, blk, SLOT_Y1) + obj_off;
-            } else if (MODE == MODE_R3A) {
+            } else if (kCnBackward) {
                 S1p = a.D1 + gobj;
                 S2p = act_ptr(a.ws, L, net, blk, SLOT_Y1) + obj_off;
-                S3p = act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off;
+                S3p = act_ptr(a.ws, L, net, blk, MODE == MODE_R3F ? SLOT_X : SLOT_P) + obj_off;
             } else {
                 S1p = a.DP + gobj;
                 S2p = nullptr;
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                             g[q] = s2.y * (dyh - sb.x - yh * sb.y);
                             h[q] = (b3[u].v[q] - s1.x) * s1.y;
                         }
-                    } else if (MODE == MODE_R3A) {
+                    } else if (kCnBackward) {
                         const float2 s1 = st1_s[c], sb = sb_s[c];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -391,13 +399,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                 a.bstat[(((int64_t)net * 2 + 1) * L.N + obj) * T * CH + (int64_t)tile * CH + tid] =
                     make_float2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y));
             }
-            float* Out = (MODE == MODE_R2 ? a.D1 : (MODE == MODE_R3A ? a.DP : a.G)) + gobj + tile * TE;
+            float* Out = (MODE == MODE_R2 ? a.D1 : (MODE == MODE_R3A ? a.DP : a.G)) + gobj + tile * TE;   // R3B, R3F: a.G
 #pragma unroll 4
             for (int i = 0; i < 8; ++i) {
                 const int r = warp * 8 + i;
                 float4 val = stage[r * 32 + (lane ^ (r & 31))];
                 float* dst = Out + (int64_t)r * EP + lane * 4;
-                if (MODE == MODE_R3B) {                      // residual path: dx = Wp^T dP + G
+                if (kResidual) {                             // residual path: dx = W^T dy + G
                     const float4 g = *reinterpret_cast<const float4*>(dst);
                     val.x += g.x; val.y += g.y; val.z += g.z; val.w += g.w;
                 }
@@ -486,12 +494,16 @@ __global__ void __launch_bounds__(256) conv_in_bwd_tc_kernel(BwdTcArgs a) {
 
 // Sum the per-CTA partials of one (matrix, net) in CTA order into the gradient blob (transposed back to the
 // blob's [in][out] layout); the block's conv biases get exact zeros.
+// blockIdx.y = 0: conv2 (which = 2) into the blob; blockIdx.y = 1: the folded layer (partials of slot 1) into a.dwf.
 __global__ void __launch_bounds__(256) reduce_wgrad_tc_kernel(BwdTcArgs a, int blk, int ctas, float* __restrict__ g4, float* __restrict__ g6) {
-    const int which = blockIdx.y, net = blockIdx.z;
+    const int which = blockIdx.y == 0 ? 2 : 1, net = blockIdx.z;
     const int t = blockIdx.x * 256 + threadIdx.x;          // t = o * 128 + i
     const int cin = net == 0 ? 4 : 6;
     float* g = net == 0 ? g4 : g6;
-    if (t < CH) g[blob_b(cin, blk, which) + t] = 0.f;
+    if (t < CH) {                                           // the block's three conv biases: exact zeros
+        if (which == 2) g[blob_b(cin, blk, 2) + t] = 0.f;
+        else { g[blob_b(cin, blk, 0) + t] = 0.f; g[blob_b(cin, blk, 1) + t] = 0.f; }
+    }
     if (t >= CH * CH) return;
     const float* p = a.wpart + (((int64_t)which * 2 + net) * ctas) * (CH * CH) + t;
     float s0 = 0.f, s1 = 0.f;
@@ -502,7 +514,30 @@ __global__ void __launch_bounds__(256) reduce_wgrad_tc_kernel(BwdTcArgs a, int b
     }
     if (i < ctas) s0 += p[(int64_t)i * CH * CH];
     const int o = t / CH, in = t % CH;
-    g[blob_w(cin, blk, which) + (int64_t)in * CH + o] = s0 + s1;
+    if (which == 2) g[blob_w(cin, blk, 2) + (int64_t)in * CH + o] = s0 + s1;
+    else a.dwf[(int64_t)net * CH * CH + (int64_t)in * CH + o] = s0 + s1;
+}
+
+// Chain rule through the fold Wf^T = Wp^T . W1^T (blob layouts [in][mid], [mid][out]):
+//   dWp^T = dWf^T . W1^T^T,   dW1^T = Wp^T^T . dWf^T        blockIdx.y: 0 -> dWp, 1 -> dW1
+// (the bias term of dW1, (sum_e dy1) bp^T, vanishes with the context norm that follows: sum_e dy1 = 0.)
+__global__ void __launch_bounds__(256) fold_wgrad_kernel(BwdTcArgs a, int blk, float* __restrict__ g4, float* __restrict__ g6) {
+    const int net = blockIdx.z, cin = net == 0 ? 4 : 6;
+    const float* prm = a.params[net];
+    const float* Wp = prm + blob_w(cin, blk, 0);            // [in][mid]
+    const float* W1 = prm + blob_w(cin, blk, 1);            // [mid][out]
+    const float* dWf = a.dwf + (int64_t)net * CH * CH;      // [in][out]
+    float* g = net == 0 ? g4 : g6;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int r = t / CH, c = t % CH;
+    float acc = 0.f;
+    if (blockIdx.y == 0) {                                  // dWp^T[in r][mid c] = sum_o dWf^T[r][o] W1^T[c][o]
+        for (int o = 0; o < CH; ++o) acc = fmaf(dWf[r * CH + o], W1[c * CH + o], acc);
+        g[blob_w(cin, blk, 0) + t] = acc;
+    } else {                                                // dW1^T[mid r][out c] = sum_i Wp^T[i][r] dWf^T[i][c]
+        for (int i = 0; i < CH; ++i) acc = fmaf(Wp[i * CH + r], dWf[i * CH + c], acc);
+        g[blob_w(cin, blk, 1) + t] = acc;
+    }
 }
 
 __global__ void __launch_bounds__(128) reduce_conv_in_tc_kernel(BwdTcArgs a, float* __restrict__ g4, float* __restrict__ g6) {
@@ -520,7 +555,7 @@ __global__ void __launch_bounds__(128) reduce_conv_in_tc_kernel(BwdTcArgs a, flo
 }
 
 struct BwdTcScratch {
-    int64_t G, D1, DP, bstat, wpart, inpart, gmax, total;   // float offsets
+    int64_t G, D1, DP, bstat, wpart, inpart, gmax, dwf, total;   // float offsets
 };
 
 BwdTcScratch bwd_tc_layout(const WsLayout& L, int ctas) {
@@ -529,11 +564,12 @@ BwdTcScratch bwd_tc_layout(const WsLayout& L, int ctas) {
     auto take = [&](int64_t n) { int64_t r = o; o += (n + 63) & ~(int64_t)63; return r; };
     s.G = take(2 * L.act);
     s.D1 = take(2 * L.act);
-    s.DP = take(2 * L.act);
+    s.DP = take(64);                                        // (gradient w.r.t. the preconv output: unused since the fold)
     s.bstat = take((int64_t)2 * 2 * L.stat * 2);
     s.wpart = take((int64_t)3 * 2 * ctas * CH * CH);
     s.inpart = take((int64_t)2 * L.N * L.T * CH * 8);
     s.gmax = take((int64_t)2 * (3 * L.depth + 1));
+    s.dwf = take((int64_t)2 * CH * CH);
     s.total = o;
     return s;
 }
@@ -575,9 +611,10 @@ int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float
     a.wpart = scratch + S.wpart;
     a.inpart = scratch + S.inpart;
     a.gmax = scratch + S.gmax;
+    a.dwf = scratch + S.dwf;
+    a.fold = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(a.scales) + tc_fold_offset_bytes(depth));
     cudaFuncSetAttribute(mlp_bwd_tc_kernel<MODE_R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem);
-    cudaFuncSetAttribute(mlp_bwd_tc_kernel<MODE_R3A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem);
-    cudaFuncSetAttribute(mlp_bwd_tc_kernel<MODE_R3B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem);
+    cudaFuncSetAttribute(mlp_bwd_tc_kernel<MODE_R3F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem);
 
     const int ng = 2 * (3 * depth + 1);
     bwd_tc_init_kernel<<<(ng + 127) / 128, 128, 0, st>>>(a.gmax, ng);
@@ -585,13 +622,13 @@ int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float
     edge_weight_bwd_tc_kernel<<<g0, 256, 0, st>>>(a, grad_reg_w);
     const dim3 tgrid((unsigned)(a.L.T * N), 2);
     const dim3 grid((unsigned)ctas, 2);
-    const dim3 rgrid((CH * CH + 255) / 256, 3, 2);
+    const dim3 rgrid((CH * CH + 255) / 256, 2, 2);
     for (int blk = depth - 1; blk >= 0; --blk) {
         cn2_bwd_sums_tc_kernel<<<tgrid, 256, 0, st>>>(a, blk);
         mlp_bwd_tc_kernel<MODE_R2><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
-        mlp_bwd_tc_kernel<MODE_R3A><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
-        mlp_bwd_tc_kernel<MODE_R3B><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
+        mlp_bwd_tc_kernel<MODE_R3F><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
         reduce_wgrad_tc_kernel<<<rgrid, 256, 0, st>>>(a, blk, ctas, grad4, grad6);
+        fold_wgrad_kernel<<<rgrid, 256, 0, st>>>(a, blk, grad4, grad6);
     }
     conv_in_bwd_tc_kernel<<<tgrid, 256, 0, st>>>(a);
     reduce_conv_in_tc_kernel<<<dim3(7, 2), 128, 0, st>>>(a, grad4, grad6);

@@ -66,6 +66,45 @@ __global__ void __launch_bounds__(256) tc_weight_scales_kernel(const float* __re
     }
 }
 
+// Folded layer of every block (see FOLD_STRIDE): Wf^T = Wp^T . W1^T and bf = W1 . bp + b1 with FP64 accumulation, rounded
+// once to FP32, plus the FP16 scale of Wf in the scales slot of conv1 (the separate preconv / conv1 scales are unused).
+__global__ void __launch_bounds__(1024) tc_fold_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
+                                                            float* __restrict__ fold, float2* __restrict__ scales) {
+    __shared__ float red[32];
+    const int m = blockIdx.x;                               // (net, blk)
+    const int blk = m % depth, net = m / depth;
+    const int cin = net == 0 ? 4 : 6;
+    const float* prm = net == 0 ? p4 : p6;
+    const float* Wp = prm + blob_w(cin, blk, 0);            // [in][mid]
+    const float* W1 = prm + blob_w(cin, blk, 1);            // [mid][out]
+    float* out = fold + (int64_t)m * FOLD_STRIDE;
+    const int tid = threadIdx.x, o = tid & 127;
+    float mx = 0.f;
+    for (int i = tid >> 7; i < CH; i += 8) {
+        double acc = 0.0;
+        for (int k = 0; k < CH; ++k) acc = fma((double)Wp[i * CH + k], (double)W1[k * CH + o], acc);
+        const float w = (float)acc;
+        out[i * CH + o] = w;
+        mx = fmaxf(mx, fabsf(w));
+    }
+    if (tid < CH) {
+        const float* bp = prm + blob_b(cin, blk, 0);
+        double acc = (double)prm[blob_b(cin, blk, 1) + tid];
+        for (int k = 0; k < CH; ++k) acc = fma((double)bp[k], (double)W1[k * CH + tid], acc);
+        out[CH * CH + tid] = (float)acc;
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        mx = 0.f;
+        for (int w = 0; w < 32; ++w) mx = fmaxf(mx, red[w]);
+        int e = 0;
+        if (mx > 0.f) frexpf(mx, &e);
+        scales[m * 3 + 1] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
@@ -105,14 +144,13 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
     const float2 sc0 = __ldg(scales + mat0);
     const float2 sc1 = (MODE != MODE_B) ? __ldg(scales + mat0 + 1) : make_float2(0.f, 0.f);
-    if (MODE == MODE_B) {
-        if (group == 0)
+    // FIRST / CA run the block's folded preconv.conv1 layer (Wf, bf from the fold area), B runs conv2
+    const float* foldp = a.fold + ((int64_t)net * L.depth + blk) * FOLD_STRIDE;
+    if (group == 0) {
+        if (MODE == MODE_B)
             load_weight_row_to_tmem(prm + blob_w(cin, blk, 2), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO, hsel);
-    } else {
-        if (group == 0)
-            load_weight_row_to_tmem(prm + blob_w(cin, blk, 0), sc0.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO, hsel);
         else
-            load_weight_row_to_tmem(prm + blob_w(cin, blk, 1), sc1.x, ch, tmem_base + lane_off + TM_W1_HI, tmem_base + lane_off + TM_W1_LO, hsel);
+            load_weight_row_to_tmem(foldp, sc1.x, ch, tmem_base + lane_off + TM_W0_HI, tmem_base + lane_off + TM_W0_LO, hsel);
     }
     tc_fence_before();
     __syncthreads();
@@ -121,8 +159,8 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     const uint32_t tmem_d = tmem_base + (group == 0 ? TM_D0 : TM_D1);
     const uint32_t t_lane = tmem_d + lane_off + (uint32_t)(hsel * 64);
     const float un0 = sc0.y, un1 = sc1.y;
-    const float bias0 = __ldg(prm + blob_b(cin, blk, w0) + ch);
-    const float bias1 = (MODE != MODE_B) ? __ldg(prm + blob_b(cin, blk, 1) + ch) : 0.f;
+    const float bias0 = (MODE == MODE_B) ? __ldg(prm + blob_b(cin, blk, 2) + ch) : 0.f;
+    const float bias1 = (MODE != MODE_B) ? __ldg(foldp + CH * CH + ch) : 0.f;
 
     // contiguous tile range of this (CTA, group): consecutive tiles share the object's statistics
     const int64_t ntiles = L.N * (int64_t)T;
@@ -283,43 +321,6 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
         mma_phase ^= 1;
         tc_fence_after();
 
-        if (MODE != MODE_B) {
-            // preconv output: + bias, kept on chip as the operand of conv1
-            float* Pg = L.save ? act_ptr(a.ws, L, net, blk, SLOT_P) + obj_off + (int64_t)ch * EP + tile * TE + hsel * 64 : nullptr;
-#pragma unroll 1
-            for (int part = 0; part < 2; ++part) {
-                float v[32];
-                tmem_ld32(t_lane + part * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], un0, bias0);
-                if (Pg != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(Pg + part * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
-#pragma unroll
-                for (int bq = 0; bq < 4; ++bq) {
-                    const float w8[8] = {v[bq * 8], v[bq * 8 + 1], v[bq * 8 + 2], v[bq * 8 + 3],
-                                         v[bq * 8 + 4], v[bq * 8 + 5], v[bq * 8 + 6], v[bq * 8 + 7]};
-                    store_b8(B_hi, B_lo, ch, hsel * 8 + part * 4 + bq, w8);
-                }
-            }
-            fence_async_smem();
-            tc_fence_before();
-            group_sync(group);
-            // ---- GEMM 2 (conv1)
-            if (gwarp == 0) {
-                if (elect_one()) {
-                    tc_fence_after();
-                    issue_layer_gemm(tmem_d, tmem_base + TM_W1_HI, tmem_base + TM_W1_LO, smem_u32(B_hi), smem_u32(B_lo));
-                    umma_commit(bar_mma);
-                }
-                __syncwarp();
-            }
-            mbar_wait(bar_mma, mma_phase);
-            mma_phase ^= 1;
-            tc_fence_after();
-        }
         // ---- final epilogue of the segment: + bias, tile statistics (thread = channel, all 128 edges), then a
         //      coalesced store: the FP32 tile is staged in this group's (now idle) operand buffer, one 512-byte
         //      row per channel with the 16-byte slots XOR-swizzled by the row so that both the row-owner writes
@@ -461,9 +462,12 @@ size_t gmw_fused_image_bytes(int depth);
 int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st);
 
 static size_t tc_scales_bytes(int depth) { return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256; }
-// bytes appended to the MLP workspace: per-matrix FP16 scales (scale, 1/scale) + the pre-split weight image
-// of the fused forward
-size_t tc_weight_image_bytes(int depth) { return tc_scales_bytes(depth) + gmw_fused_image_bytes(depth); }
+static size_t tc_fold_bytes(int depth) { return (((size_t)2 * depth * FOLD_STRIDE * sizeof(float)) + 255) / 256 * 256; }
+// byte offset (from the scales) of the folded layers of the layer-wise kernels
+size_t tc_fold_offset_bytes(int depth) { return tc_scales_bytes(depth) + gmw_fused_image_bytes(depth); }
+// bytes appended to the MLP workspace: per-matrix FP16 scales (scale, 1/scale), the tail of the fused forward (its
+// own scales, biases, pre-split weight image, exchange buffer), the folded layers of the layer-wise kernels
+size_t tc_weight_image_bytes(int depth) { return tc_fold_offset_bytes(depth) + tc_fold_bytes(depth); }
 
 // DCD_B200_LAYERWISE=1 forces the layer-wise kernels also for inference (A/B measurements, cross-checks)
 static bool force_layerwise() {
@@ -482,6 +486,7 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     a.params[0] = params4; a.params[1] = params6;
     a.ws = ws;
     a.L = make_layout(N, n, depth, save);
+    a.fold = nullptr;
     if ((int64_t)a.L.T * N > 0x7fffffffLL) return DCD_E_UNSUPPORTED;
     // the scales live right after the layout's own area (256-byte aligned)
     float2* scales = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(ws) +
@@ -496,6 +501,9 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
         return DCD_OK;
     }
     tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
+    float* fold = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scales) + tc_fold_offset_bytes(depth));
+    tc_fold_prep_kernel<<<2 * depth, 1024, 0, st>>>(params4, params6, depth, fold, scales);
+    a.fold = fold;
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
