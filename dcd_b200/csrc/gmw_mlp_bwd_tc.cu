@@ -522,22 +522,44 @@ __global__ void __launch_bounds__(256) reduce_wgrad_tc_kernel(BwdTcArgs a, int b
 //   dWp^T = dWf^T . W1^T^T,   dW1^T = Wp^T^T . dWf^T        blockIdx.y: 0 -> dWp, 1 -> dW1
 // (the bias term of dW1, (sum_e dy1) bp^T, vanishes with the context norm that follows: sum_e dy1 = 0.)
 __global__ void __launch_bounds__(256) fold_wgrad_kernel(BwdTcArgs a, int blk, float* __restrict__ g4, float* __restrict__ g6) {
+    // 32 x 32 output tile per block, 32-deep chunks of the contraction staged in shared memory (both products read their
+    // operands along the contiguous index; the A . B^T one is transposed on the way in)
+    __shared__ float As[32][33], Bs[32][33];
     const int net = blockIdx.z, cin = net == 0 ? 4 : 6;
     const float* prm = a.params[net];
     const float* Wp = prm + blob_w(cin, blk, 0);            // [in][mid]
     const float* W1 = prm + blob_w(cin, blk, 1);            // [mid][out]
     const float* dWf = a.dwf + (int64_t)net * CH * CH;      // [in][out]
     float* g = net == 0 ? g4 : g6;
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    const int r = t / CH, c = t % CH;
-    float acc = 0.f;
-    if (blockIdx.y == 0) {                                  // dWp^T[in r][mid c] = sum_o dWf^T[r][o] W1^T[c][o]
-        for (int o = 0; o < CH; ++o) acc = fmaf(dWf[r * CH + o], W1[c * CH + o], acc);
-        g[blob_w(cin, blk, 0) + t] = acc;
-    } else {                                                // dW1^T[mid r][out c] = sum_i Wp^T[i][r] dWf^T[i][c]
-        for (int i = 0; i < CH; ++i) acc = fmaf(Wp[i * CH + r], dWf[i * CH + c], acc);
-        g[blob_w(cin, blk, 1) + t] = acc;
+    const bool first = blockIdx.y == 0;                     // dWp^T[in r][mid c] = sum_o dWf^T[r][o] W1^T[c][o]
+    const int r0 = (blockIdx.x >> 2) * 32, c0 = (blockIdx.x & 3) * 32;   // else dW1^T[mid r][out c] = sum_i Wp^T[i][r] dWf^T[i][c]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 8 rows of 32 threads
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < CH; k0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int y = ty + 8 * q;
+            if (first) {
+                As[y][tx] = dWf[(r0 + y) * CH + k0 + tx];    // As[r][k]
+                Bs[y][tx] = W1[(c0 + y) * CH + k0 + tx];     // Bs[c][k]
+            } else {
+                As[y][tx] = Wp[(k0 + y) * CH + r0 + tx];     // As[k][r]
+                Bs[y][tx] = dWf[(k0 + y) * CH + c0 + tx];    // Bs[k][c]
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int y = ty + 8 * q;
+                acc[q] = first ? fmaf(As[y][k], Bs[tx][k], acc[q]) : fmaf(As[k][y], Bs[k][tx], acc[q]);
+            }
+        }
+        __syncthreads();
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[blob_w(cin, blk, first ? 0 : 1) + (r0 + ty + 8 * q) * CH + c0 + tx] = acc[q];
 }
 
 __global__ void __launch_bounds__(128) reduce_conv_in_tc_kernel(BwdTcArgs a, float* __restrict__ g4, float* __restrict__ g6) {
@@ -628,7 +650,7 @@ int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float
         mlp_bwd_tc_kernel<MODE_R2><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
         mlp_bwd_tc_kernel<MODE_R3F><<<grid, BT_THREADS, kBwdTcSmem, st>>>(a, blk);
         reduce_wgrad_tc_kernel<<<rgrid, 256, 0, st>>>(a, blk, ctas, grad4, grad6);
-        fold_wgrad_kernel<<<rgrid, 256, 0, st>>>(a, blk, grad4, grad6);
+        fold_wgrad_kernel<<<dim3(16, 2, 2), 256, 0, st>>>(a, blk, grad4, grad6);
     }
     conv_in_bwd_tc_kernel<<<tgrid, 256, 0, st>>>(a);
     reduce_conv_in_tc_kernel<<<dim3(7, 2), 128, 0, st>>>(a, grad4, grad6);

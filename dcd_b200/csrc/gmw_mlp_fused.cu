@@ -192,14 +192,14 @@ __device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, u
 
 // Layer matrices of the fused forward.  There is no non-linearity between a block's preconv and conv1
 // (ops.py:125-131: x = preconv(x); x = conv1(x) -> context norm), so the two 128x128 layers are folded into one:
-//     Wf = W1 . Wp,   bf = W1 . bp + b1        (FP64 accumulation, rounded once to FP32)
+//     Wf = W1 . Wp,   bf = W1 . bp + b1        (FP64 accumulation, rounded once to FP32; tc_fold_prep_kernel)
 // which removes a third of the GEMM layers (24 instead of 36 per net; SURVEY 8d: report F_m with 24).
 // Per matrix m = (net, block, j) with j = 0: Wf, j = 1: W2 this kernel writes the power-of-two FP16 scale, the bias
 // and the pre-split weight image [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1) of
 // scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
 __global__ void __launch_bounds__(1024) fused_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
-                                                         float2* __restrict__ scales2, float* __restrict__ bias2,
-                                                         uint32_t* __restrict__ img) {
+                                                         const float* __restrict__ fold, float2* __restrict__ scales2,
+                                                         float* __restrict__ bias2, uint32_t* __restrict__ img) {
     extern __shared__ float wf_s[];                           // [in][out] FP32, 64 KB
     __shared__ float red[32];
     __shared__ float scale_s;
@@ -208,21 +208,10 @@ __global__ void __launch_bounds__(1024) fused_prep_kernel(const float* __restric
     const int cin = net == 0 ? 4 : 6;
     const float* prm = net == 0 ? p4 : p6;
     const int tid = threadIdx.x;
-    if (j == 0) {
-        const float* Wp = prm + blob_w(cin, blk, 0);          // [in][mid]
-        const float* W1 = prm + blob_w(cin, blk, 1);          // [mid][out]
-        const int o = tid & 127;
-        for (int i = tid >> 7; i < CH; i += 8) {
-            double acc = 0.0;
-            for (int k = 0; k < CH; ++k) acc = fma((double)Wp[i * CH + k], (double)W1[k * CH + o], acc);
-            wf_s[i * CH + o] = (float)acc;
-        }
-        if (tid < CH) {
-            const float* bp = prm + blob_b(cin, blk, 0);
-            double acc = (double)prm[blob_b(cin, blk, 1) + tid];
-            for (int k = 0; k < CH; ++k) acc = fma((double)bp[k], (double)W1[k * CH + tid], acc);
-            bias2[m * CH + tid] = (float)acc;
-        }
+    if (j == 0) {                                            // folded layer, formed by tc_fold_prep_kernel (gmw_mlp_tc.cu)
+        const float* F = fold + ((int64_t)net * depth + blk) * FOLD_STRIDE;
+        for (int i = tid; i < CH * CH; i += 1024) wf_s[i] = F[i];
+        if (tid < CH) bias2[m * CH + tid] = F[CH * CH + tid];
     } else {
         const float* W2 = prm + blob_w(cin, blk, 2);
         for (int i = tid; i < CH * CH; i += 1024) wf_s[i] = W2[i];
@@ -786,7 +775,7 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
         max_groups_of[dev] = g;
     }
     const int max_groups = max_groups_of[dev];
-    fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, scales2, bias2, wimg);
+    fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, a.fold, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;
     const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);

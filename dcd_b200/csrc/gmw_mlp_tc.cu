@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(256) tc_weight_scales_kernel(const float* __re
 }
 
 // Folded layer of every block (see FOLD_STRIDE): Wf^T = Wp^T . W1^T and bf = W1 . bp + b1 with FP64 accumulation, rounded
-// once to FP32, plus the FP16 scale of Wf in the scales slot of conv1 (the separate preconv / conv1 scales are unused).
+// once to FP32.  grid (8, 2 * depth): block (bx, m) forms rows [16 bx, 16 bx + 16) of matrix m = (net, blk) and raises the
+// matrix' running maximum (float bits, >= 0) in wmax[m]; wmax must be zero before the launch.
 __global__ void __launch_bounds__(1024) tc_fold_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
-                                                            float* __restrict__ fold, float2* __restrict__ scales) {
-    __shared__ float red[32];
-    const int m = blockIdx.x;                               // (net, blk)
+                                                            float* __restrict__ fold, int* __restrict__ wmax) {
+    const int m = blockIdx.y;                               // (net, blk)
     const int blk = m % depth, net = m / depth;
     const int cin = net == 0 ? 4 : 6;
     const float* prm = net == 0 ? p4 : p6;
@@ -80,29 +80,31 @@ __global__ void __launch_bounds__(1024) tc_fold_prep_kernel(const float* __restr
     float* out = fold + (int64_t)m * FOLD_STRIDE;
     const int tid = threadIdx.x, o = tid & 127;
     float mx = 0.f;
-    for (int i = tid >> 7; i < CH; i += 8) {
+    for (int i = 16 * blockIdx.x + (tid >> 7); i < 16 * blockIdx.x + 16; i += 8) {
         double acc = 0.0;
+#pragma unroll 8
         for (int k = 0; k < CH; ++k) acc = fma((double)Wp[i * CH + k], (double)W1[k * CH + o], acc);
         const float w = (float)acc;
         out[i * CH + o] = w;
         mx = fmaxf(mx, fabsf(w));
     }
-    if (tid < CH) {
+    if (blockIdx.x == 0 && tid < CH) {
         const float* bp = prm + blob_b(cin, blk, 0);
         double acc = (double)prm[blob_b(cin, blk, 1) + tid];
         for (int k = 0; k < CH; ++k) acc = fma((double)bp[k], (double)W1[k * CH + tid], acc);
         out[CH * CH + tid] = (float)acc;
     }
     mx = warp_max(mx);
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        mx = 0.f;
-        for (int w = 0; w < 32; ++w) mx = fmaxf(mx, red[w]);
-        int e = 0;
-        if (mx > 0.f) frexpf(mx, &e);
-        scales[m * 3 + 1] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
-    }
+    if ((tid & 31) == 0) atomicMax(wmax + m, __float_as_int(mx));
+}
+// FP16 scale of every folded layer into the scales slot of conv1 (the separate preconv / conv1 scales are unused)
+__global__ void tc_fold_scale_kernel(const int* __restrict__ wmax, int nmat, float2* __restrict__ scales) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmat) return;
+    const float mx = __int_as_float(wmax[m]);
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    scales[m * 3 + 1] = make_float2(ldexpf(1.f, 10 - e), ldexpf(1.f, e - 10));
 }
 
 template <int MODE>
@@ -462,7 +464,18 @@ size_t gmw_fused_image_bytes(int depth);
 int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st);
 
 static size_t tc_scales_bytes(int depth) { return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256; }
-static size_t tc_fold_bytes(int depth) { return (((size_t)2 * depth * FOLD_STRIDE * sizeof(float)) + 255) / 256 * 256; }
+static size_t tc_fold_bytes(int depth) {                  // folded layers + their running maxima (one int per matrix)
+    return (((size_t)2 * depth * FOLD_STRIDE * sizeof(float)) + 255) / 256 * 256 + (((size_t)2 * depth * sizeof(int)) + 255) / 256 * 256;
+}
+// forms the folded layers in the workspace tail (used by the layer-wise kernels and, as input, by the fused forward's prep)
+float* launch_fold_prep(const float* params4, const float* params6, int depth, float2* scales, bool want_scales, cudaStream_t st) {
+    float* fold = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth) + gmw_fused_image_bytes(depth));
+    int* wmax = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(fold) + (((size_t)2 * depth * FOLD_STRIDE * sizeof(float)) + 255) / 256 * 256);
+    cudaMemsetAsync(wmax, 0, (size_t)2 * depth * sizeof(int), st);
+    tc_fold_prep_kernel<<<dim3(8, 2 * depth), 1024, 0, st>>>(params4, params6, depth, fold, wmax);
+    if (want_scales) tc_fold_scale_kernel<<<1, 64, 0, st>>>(wmax, 2 * depth, scales);
+    return fold;
+}
 // byte offset (from the scales) of the folded layers of the layer-wise kernels
 size_t tc_fold_offset_bytes(int depth) { return tc_scales_bytes(depth) + gmw_fused_image_bytes(depth); }
 // bytes appended to the MLP workspace: per-matrix FP16 scales (scale, 1/scale), the tail of the fused forward (its
@@ -494,6 +507,7 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     const unsigned g2 = (unsigned)(((a.L.E + 255) / 256) * N);
     if (!save && gmw_fused_supported(n) && !force_layerwise()) {
         // inference: whole network on chip, one kernel (gmw_mlp_fused.cu)
+        a.fold = launch_fold_prep(params4, params6, depth, scales, false, st);
         const int rc = launch_gmw_fused_fwd(a, params4, params6, reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth), st);
         if (rc != DCD_OK) return rc;
         gmw_edge_weight_kernel<true><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
@@ -501,9 +515,7 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
         return DCD_OK;
     }
     tc_weight_scales_kernel<<<2 * depth * 3, 256, 0, st>>>(params4, params6, depth, scales);
-    float* fold = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scales) + tc_fold_offset_bytes(depth));
-    tc_fold_prep_kernel<<<2 * depth, 1024, 0, st>>>(params4, params6, depth, fold, scales);
-    a.fold = fold;
+    a.fold = launch_fold_prep(params4, params6, depth, scales, true, st);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     cudaFuncSetAttribute(mlp_tc_kernel<MODE_CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
