@@ -255,8 +255,8 @@ def main():
                 mlp_events.append((e0, e1, nc))
             check(L.dcd_gmw_aggregate_fwd(ptr(regw), ptr(zsel), ptr(idx), nc, EDGES, K_SEL, 1, ptr(depth_out[c0:]), 0, st),
                   "aggregate")
-            # select | layer folding + weight image, fused MLP (all layers of both nets), edge weights | aggregate
-            launches[0] += 1 + 3 + 1
+            # select | layer folding, weight image, fused MLP (all layers of both nets), edge weights | aggregate
+            launches[0] += 1 + 4 + 1
 
     def gather():
         if world > 1:
