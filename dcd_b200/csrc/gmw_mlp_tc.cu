@@ -1,7 +1,11 @@
-// GMW edge-feature MLP forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// GMW edge-feature MLP forward, layer by layer, on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a:
+// the training forward (activations saved for the backward) and the inference forward for n > 73; inference at
+// n <= 73 runs gmw_mlp_fused.cu instead.
 //
-// Same segment structure as the CUDA-core version (FIRST / B / CA between context-norm barriers), but
-// the 128x128x128 layer GEMMs run as tcgen05.mma with FP32 accumulation in tensor memory:
+// The net is cut at the context norms into segments, each one persistent launch over all (object, 128-edge tile) pairs:
+// FIRST conv_in -> Wf, B CN -> conv2, CA CN + ReLU + residual -> Wf, where Wf = W1 . Wp is the block's preconv and conv1
+// folded into one layer (nothing sits between them, ops.py:125-131; tc_fold_prep_kernel).  The 128x128x128 layer GEMMs
+// run as tcgen05.mma with FP32 accumulation in tensor memory:
 //   D[out-channel (TMEM lane) x edge (TMEM column)] = W[out x in] . X[in x edge]
 // FP32 fidelity comes from a two-term FP16 split of BOTH operands (x = hi + lo, 11 + 11 significant
 // bits) and three MMAs per product:  D = Wh.Xl + Wl.Xh + Wh.Xh   (the dropped Wl.Xl term is 2^-22).
@@ -11,12 +15,10 @@
 //     TENSOR MEMORY as the A operand while the persistent CTA loops over its tiles (one CTA per SM,
 //     74 per net).  With A in shared memory an M = N = 128 MMA would need all 128 B/clk of shared-memory
 //     bandwidth; from tensor memory only B is fetched;
-//   * B (activations) is written straight into the canonical MN-major no-swizzle layout by the threads
-//     that produce it (thread = input channel, 16-byte stores of 8 edges: conflict free), both for the
-//     tile source (context norm + ReLU + residual fused into the load) and for the chained preconv
-//     output, which never leaves the SM;
+//   * B (activations) is written straight into the canonical MN-major 128B-swizzled layout by the threads
+//     that load the tile (context norm + ReLU + residual fused into the load);
 //   * the epilogue reads D with tcgen05.ld (32 lanes x 32 columns per warp): a thread owns one output
-//     channel, so bias, context-norm statistics and the split for the next GEMM need no shuffles.
+//     channel, so bias and context-norm statistics need no shuffles.
 #include <cstdlib>
 #include "gmw_tc_common.cuh"
 
@@ -130,7 +132,7 @@ mlp_tc_kernel(MlpArgs a, int blk, const float2* __restrict__ scales) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);
 
     // ---- one-time setup: barriers, tensor memory, resident weights
-    const int w0 = (MODE == MODE_B) ? 2 : 0;                // first matrix of this segment (conv2 | preconv)
+    const int w0 = (MODE == MODE_B) ? 2 : 0;                // scales slot of this segment's matrix: conv2 | (slot 0 + 1 =) folded layer
     const int mat0 = (net * L.depth + blk) * 3 + w0;
     if (tid == 0) {
         mbar_init(reinterpret_cast<uint64_t*>(smem + SM_BAR), 1);
