@@ -85,6 +85,10 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
             raise RuntimeError("dcd_b200 ops need all tensors on one device")
     if dev is None:
         raise RuntimeError("dcd_b200 ops need at least one CUDA tensor")
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        # the library launches on the CURRENT device and stream (include/dcd_b200.h)
+        raise RuntimeError("dcd_b200 ops run on the current CUDA device (cuda:%d) but the tensors live on %s; "
+                           "wrap the call in `with torch.cuda.device(t.device):`" % (torch.cuda.current_device(), dev))
     return dev
 
 

@@ -248,8 +248,152 @@ edge_solve_fwd_warp_kernel(const float* __restrict__ kps, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// selection: top-k edges by |V| sorted (|V| desc, edge id asc) + their depths / pair masks / mean.
-// One CTA per object; bitonic sort of (key, id) in shared memory.
+// forward, mean only, throughput variant (large N): a warp owns a GROUP of G consecutive objects.
+//
+// The edge loop is issue-bound (an IEEE-exact quotient costs 6 of the ~16 instructions of an edge), so this kernel
+// removes everything else from it:
+//   * per-keypoint terms as three separate arrays {v, Y, v*C} (12 B per keypoint; C itself is not needed forward);
+//   * lane = one (object, keypoint i) SLOT; the G objects of a group are chosen so that G*n fills whole warps
+//     (n = 73: G = 7, 511 of 512 slots busy), the slot's own terms sit in registers;
+//   * circulant enumeration: every unordered pair is {i, (i + d) mod n} for exactly one d in 1..n/2, so the slot
+//     walks d = 1 .. n/2 and reads its partner's terms at [i + d] of arrays whose first n/2 entries are repeated
+//     after the n-th (no modulo).  Consecutive lanes read consecutive words (the per-object stride is congruent
+//     to n modulo 32 so this also holds across objects of the group): 3 conflict-free LDS.32 per edge, offsets
+//     are immediates, no pair table, no index arithmetic;
+//   * |H| and |V| are symmetric in the endpoints (IEEE subtraction is antisymmetric), so every edge value is the
+//     one of the reference's (i < j) evaluation, bit for bit; only the order of the sum differs (mean: 1e-6 bar);
+//   * objects with a non-finite term take a separate loop with torch's NaN-propagating clamps.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRP_WARPS = 4;
+__host__ __device__ constexpr int grp_stride(int n) { return n + 32 * ((n / 2 + 31) / 32); }   // == n (mod 32), >= n + n/2
+__host__ __device__ constexpr int grp_warp_floats(int n, int G) { return 3 * G * grp_stride(n) + ((G * n + 31) & ~31) + 8 * G; }
+
+template <int NK, int GC>
+__global__ void __launch_bounds__(GRP_WARPS * 32)
+edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                       const float* __restrict__ rot, const float* __restrict__ K,
+                       int64_t N, int n_rt, int G_rt, float lo, float hi, int flags,
+                       float* __restrict__ depth_mean) {
+    const int n = NK > 0 ? NK : n_rt;
+    const int G = NK > 0 ? GC : G_rt;
+    const int S = grp_stride(n);
+    const int D = n / 2;                                     // offsets 1 .. D; for even n the last one covers i < n/2 only
+    const int Dfull = (n - 1) / 2;
+    const int E = n * (n - 1) / 2;
+    extern __shared__ __align__(16) float grp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* v_s = grp_smem + (size_t)warp * grp_warp_floats(n, G);
+    float* Y_s = v_s + G * S;
+    float* c_s = Y_s + G * S;
+    float* part_s = c_s + G * S;                             // [G * n] per-slot sums
+    float4* sc_s = reinterpret_cast<float4*>(part_s + ((G * n + 31) & ~31));    // [G] (sin, cos, cy, fy)
+    float* b3_s = reinterpret_cast<float*>(sc_s + G);        // [G]
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    const int64_t ngroups = (N + G - 1) / G;
+
+    for (int64_t grp = (int64_t)blockIdx.x * GRP_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * GRP_WARPS) {
+        const int64_t obj0 = grp * G;
+        const int gcount = (int)((N - obj0 < G) ? N - obj0 : G);
+        const int slots = gcount * n;
+        if (lane < gcount) {
+            const int64_t obj = obj0 + lane;
+            float cy = 0.f, fy = 1.f, b3 = 0.f;
+            if (K != nullptr) {
+                const float* Ko = K + obj * 12;
+                if (normalise) { cy = __ldg(Ko + 6); fy = __ldg(Ko + 5); }
+                if (flags & DCD_SUB_B3) b3 = __ldg(Ko + 11);
+            }
+            const float r = __ldg(rot + obj);
+            sc_s[lane] = make_float4(sinf(r), cosf(r), cy, fy);
+            b3_s[lane] = b3;
+        }
+        __syncwarp();
+        // ---- stage the group's keypoint terms: global keypoint index = obj0 * n + slot (coalesced)
+        bool bad = false;
+        const float* kv = kps + obj0 * n * 2 + 1;
+        const float* k3 = kps3d + obj0 * n * 3;
+#pragma unroll 4
+        for (int s0 = 0; s0 < slots; s0 += 32) {
+            const int s = s0 + lane;
+            if (s < slots) {
+                const int g = s / n, i = s - g * n;
+                const float4 q = sc_s[g];
+                const float4 t = keypoint_terms(__ldg(kv + 2 * s), __ldg(k3 + 3 * s), __ldg(k3 + 3 * s + 1), __ldg(k3 + 3 * s + 2),
+                                                q.x, q.y, normalise, q.z, q.w);
+                const int base = g * S + i;
+                v_s[base] = t.x; Y_s[base] = t.y; c_s[base] = t.z;
+                if (i < D) { v_s[base + n] = t.x; Y_s[base + n] = t.y; c_s[base + n] = t.z; }
+                bad |= !(fabsf(t.x) + fabsf(t.y) + fabsf(t.z) <= 3.0e38f);
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        __syncwarp();
+        // ---- edges
+        for (int s0 = 0; s0 < slots; s0 += 32) {
+            const int s = s0 + lane;
+            const bool active = s < slots;
+            const int g = active ? s / n : 0, i = active ? s - g * n : 0;
+            const float* pv = v_s + g * S + i;
+            const float* pY = pv + G * S;
+            const float* pc = pY + G * S;
+            const float vi = pv[0], Yi = pY[0], ci = pc[0];
+            float acc0 = 0.f, acc1 = 0.f;
+            if (!bad) {
+                // two partners per step on packed FP32 pairs (FADD2 / FMUL2 / FFMA2): 12 issue slots per edge instead of 17
+                const float2 vi2 = make_float2(vi, vi), Yi2 = make_float2(Yi, Yi), ci2 = make_float2(ci, ci);
+                float2 acc = make_float2(0.f, 0.f);
+                int d = 1;
+                if (NK > 0) {
+#pragma unroll
+                    for (; d + 1 <= Dfull; d += 2)
+                        acc = add2_rn(acc, edge_quotient_finite2(vi2, Yi2, ci2, make_float2(pv[d], pv[d + 1]), make_float2(pY[d], pY[d + 1]),
+                                                                 make_float2(pc[d], pc[d + 1]), lo, hi));
+                } else {
+#pragma unroll 2
+                    for (; d + 1 <= Dfull; d += 2)
+                        acc = add2_rn(acc, edge_quotient_finite2(vi2, Yi2, ci2, make_float2(pv[d], pv[d + 1]), make_float2(pY[d], pY[d + 1]),
+                                                                 make_float2(pc[d], pc[d + 1]), lo, hi));
+                }
+                acc0 = acc.x;
+                acc1 = acc.y;
+                if (d <= Dfull) acc0 += edge_quotient_finite(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi);
+                if (D > Dfull && i < D) acc1 += edge_quotient_finite(vi, Yi, ci, pv[D], pY[D], pc[D], lo, hi);
+            } else {
+#pragma unroll 1
+                for (int d = 1; d <= Dfull; ++d) acc0 += edge_quotient_ieee(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi);
+                if (D > Dfull && i < D) acc1 += edge_quotient_ieee(vi, Yi, ci, pv[D], pY[D], pc[D], lo, hi);
+            }
+            if (active) part_s[s] = acc0 + acc1;
+        }
+        __syncwarp();
+        // ---- per-object mean (fixed order: deterministic and independent of the group an object falls into)
+        for (int g = 0; g < gcount; ++g) {
+            float t = 0.f;
+            for (int i = lane; i < n; i += 32) t += part_s[g * n + i];
+            t = warp_sum(t);
+            if (lane == 0) depth_mean[obj0 + g] = __fsub_rn(__fdiv_rn(t, (float)E), b3_s[g]);
+        }
+        __syncwarp();                                        // all lanes done with the group's arrays before restaging
+    }
+}
+
+// objects per group: the G in 1..8 that fills the warps of a group best within ~12 KB of shared memory per warp
+int grp_pick_G(int n) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int G = 1; G <= 8; ++G) {
+        if (G > 1 && (size_t)grp_warp_floats(n, G) * sizeof(float) > 14 * 1024) break;
+        const int slots = G * n, rounds = (slots + 31) / 32;
+        const double eff = (double)slots / (32.0 * rounds);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = G; }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection, general k (k > 2048; the reference's k = 1500 runs edge_select.cu): top-k edges by |V| sorted
+// (|V| desc, edge id asc) + their depths / pair masks / mean.  One CTA per object; bitonic sort of all (key, id)
+// pairs in shared memory.
 // ---------------------------------------------------------------------------------------------
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -433,7 +577,30 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
     constexpr int T = 256;
     const int E = n * (n - 1) / 2;
     const int sms = device_sm_count();
-    // throughput regime: one warp per object (no per-object block barrier)
+    // throughput regime, mean only: groups of objects per warp, circulant edge enumeration (edge_mean_group_kernel)
+    if (N >= (int64_t)sms * 16 && depth_edges == nullptr) {
+        const int G = n == 73 ? 7 : grp_pick_G(n);
+        const size_t gsmem = (size_t)GRP_WARPS * grp_warp_floats(n, G) * sizeof(float);
+        const int64_t ngroups = (N + G - 1) / G;
+        const int64_t want = (ngroups + GRP_WARPS - 1) / GRP_WARPS;
+        int per_sm = (int)((227 * 1024) / (gsmem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) return DCD_E_UNSUPPORTED;
+        const int64_t cap = (int64_t)sms * per_sm;
+        const int grid = (int)(want < cap ? want : cap);
+        if (n == 73) {
+            if (gsmem > 48 * 1024)
+                cudaFuncSetAttribute(edge_mean_group_kernel<73, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+            edge_mean_group_kernel<73, 7><<<grid, GRP_WARPS * 32, gsmem, st>>>(kps, kps3d, rot, K, N, n, G, lo, hi, flags, depth_mean);
+        } else {
+            if (gsmem > 48 * 1024)
+                cudaFuncSetAttribute(edge_mean_group_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+            edge_mean_group_kernel<0, 0><<<grid, GRP_WARPS * 32, gsmem, st>>>(kps, kps3d, rot, K, N, n, G, lo, hi, flags, depth_mean);
+        }
+        DCD_CHECK_LAUNCH();
+        return DCD_OK;
+    }
+    // throughput regime with per-edge output: one warp per object (no per-object block barrier)
     const size_t wsmem = (size_t)(T / 32) * n * sizeof(float4) + (size_t)E * sizeof(uint32_t);
     if (N >= (int64_t)sms * 16 && wsmem <= 100 * 1024) {
         const int64_t want = (N + T / 32 - 1) / (T / 32), cap = (int64_t)sms * 6;
@@ -477,7 +644,7 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
     return DCD_OK;
 }
 
-int launch_edge_select(const float* kps, const float* kps3d, const float* rot, const float* K,
+int launch_edge_select_bitonic(const float* kps, const float* kps3d, const float* rot, const float* K,
                        const uint8_t* kpt_mask, int64_t N, int n, int k, float lo, float hi, int flags,
                        int64_t* idx_out, float* depth_sel, float* mask_sel, float* depth_mean, cudaStream_t st) {
     constexpr int T = 256;

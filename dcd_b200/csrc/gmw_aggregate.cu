@@ -14,13 +14,19 @@ struct Softmax {
     float mx, sum;
 };
 
+// an index outside [0, E) must not fault (torch.gather raises there; the Python wrapper validates on request)
+__device__ __forceinline__ int64_t edge_id(const int64_t* __restrict__ id_row, int r, int64_t E) {
+    const int64_t id = id_row[r];
+    return id < 0 ? 0 : (id >= E ? E - 1 : id);
+}
+
 __device__ __forceinline__ Softmax warp_softmax_stats(const float* __restrict__ w_row,
-                                                      const int64_t* __restrict__ id_row, int k, int lane) {
+                                                      const int64_t* __restrict__ id_row, int k, int64_t E, int lane) {
     float mx = -INFINITY;
-    for (int r = lane; r < k; r += 32) mx = fmaxf(mx, __ldg(w_row + id_row[r]));
+    for (int r = lane; r < k; r += 32) mx = fmaxf(mx, __ldg(w_row + edge_id(id_row, r, E)));
     mx = warp_max(mx);
     float s = 0.f;
-    for (int r = lane; r < k; r += 32) s += expf(__ldg(w_row + id_row[r]) - mx);
+    for (int r = lane; r < k; r += 32) s += expf(__ldg(w_row + edge_id(id_row, r, E)) - mx);
     s = warp_sum(s);
     return {mx, s};
 }
@@ -35,10 +41,10 @@ gmw_aggregate_fwd_kernel(const float* __restrict__ reg_w, const float* __restric
     const float* w_row = reg_w + obj * E;
     const int64_t* id_row = idx + obj * k;
     const float* z_row = depths + obj * (sel ? (int64_t)k : E);
-    const Softmax sm = warp_softmax_stats(w_row, id_row, k, lane);
+    const Softmax sm = warp_softmax_stats(w_row, id_row, k, E, lane);
     float acc = 0.f;
     for (int r = lane; r < k; r += 32) {
-        const int64_t id = id_row[r];
+        const int64_t id = edge_id(id_row, r, E);
         const float p = __fdiv_rn(expf(__ldg(w_row + id) - sm.mx), sm.sum);
         const float z = sel ? __ldg(z_row + r) : __ldg(z_row + id);
         if (probs != nullptr) probs[obj * k + r] = p;
@@ -63,10 +69,10 @@ gmw_aggregate_bwd_kernel(const float* __restrict__ reg_w, const float* __restric
     for (int64_t e = lane; e < E; e += 32) gw_row[e] = 0.f;
     if (grad_z != nullptr && !sel)
         for (int64_t e = lane; e < E; e += 32) grad_z[obj * E + e] = 0.f;
-    const Softmax sm = warp_softmax_stats(w_row, id_row, k, lane);
+    const Softmax sm = warp_softmax_stats(w_row, id_row, k, E, lane);
     float acc = 0.f;
     for (int r = lane; r < k; r += 32) {
-        const int64_t id = id_row[r];
+        const int64_t id = edge_id(id_row, r, E);
         const float p = __fdiv_rn(expf(__ldg(w_row + id) - sm.mx), sm.sum);
         const float z = sel ? __ldg(z_row + r) : __ldg(z_row + id);
         acc += z * p;
@@ -75,7 +81,7 @@ gmw_aggregate_bwd_kernel(const float* __restrict__ reg_w, const float* __restric
     const float g = __ldg(grad_out + obj);
     __syncwarp();   // orders the zero fill before the scatter
     for (int r = lane; r < k; r += 32) {
-        const int64_t id = id_row[r];
+        const int64_t id = edge_id(id_row, r, E);
         const float p = __fdiv_rn(expf(__ldg(w_row + id) - sm.mx), sm.sum);
         const float z = sel ? __ldg(z_row + r) : __ldg(z_row + id);
         gw_row[id] = g * p * (z - Zbar);

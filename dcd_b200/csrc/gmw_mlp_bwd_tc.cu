@@ -2,10 +2,10 @@
 //
 // Autograd of GMW/main.py:465 restricted to the regression path, over the activations saved by the forward
 // (block input x, preconv output P, pre-norm outputs Y1, Y2 + context-norm statistics).  Per residual block,
-// last to first, three launches of ONE templated kernel (plus the small sums kernel of the second norm):
+// last to first, two launches of ONE templated kernel (plus the small sums kernel of the second norm):
 //     R2 :  dy2 = CN'(G * relu')          dW2 += dy2 . yhat1^T     d yhat1 = W2^T dy2   (+ sums for CN1')
-//     R3A:  dy1 = CN'(d yhat1)            dW1 += dy1 . P^T         dP      = W1^T dy1
-//     R3B:  dP                            dWp += dP  . x^T         G       = Wp^T dP + G   (residual path)
+//     R3F:  dy1 = CN'(d yhat1)            dWf += dy1 . x^T         G       = Wf^T dy1 + G   (folded preconv.conv1, residual path)
+// followed by the chain rule through the fold (fold_wgrad_kernel: dWp, dW1 from dWf).
 // Every launch is the same dataflow on a 128-edge tile:
 //   * the gradient operand A1 (128 channels x 128 edges) and the activation operand A2 are written ONCE into
 //     shared memory as FP16 hi/lo images in the 128B-swizzled layout of the forward; the same A1 image is the
@@ -33,7 +33,6 @@ struct BwdTcArgs {
     float* dwf;             // [2][128*128] gradient of the folded layer, blob layout [in][out]
     float* G;               // [2][N][128][EP] gradient w.r.t. the current block output
     float* D1;              // [2][N][128][EP] gradient w.r.t. yhat1
-    float* DP;              // [2][N][128][EP] gradient w.r.t. the preconv output
     float2* bstat;          // [2][2][N][T][128] partial sums of the context-norm backward
     float* wpart;           // [3][2 * ctas][128*128] per-CTA partial weight gradients
     float* inpart;          // [2*N*T][128][8] partial conv_in gradients
@@ -45,8 +44,7 @@ size_t tc_fold_offset_bytes(int depth);
 namespace {
 
 // R2: dy2, dW2, dyhat1.  R3F: dy1 (context-norm backward), dWf, dx + residual for the folded preconv.conv1 layer.
-// (R3A / R3B are the same two steps for the unfolded pair of layers; kept for reference, not launched.)
-enum { MODE_R2 = 0, MODE_R3A = 1, MODE_R3B = 2, MODE_R3F = 3 };
+enum { MODE_R2 = 0, MODE_R3F = 3 };
 constexpr int BT_THREADS = 512;
 constexpr uint32_t TMB_W_HI = 0, TMB_W_LO = 64, TMB_DW = 128, TMB_D = 256;
 constexpr size_t SMB_A1 = 0;                                       // gradient image  {hi, lo} 64 KB (also the output staging)
@@ -218,9 +216,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMB_BAR + 16);
 
     // ---- setup: barrier, tensor memory, W^T resident as the A operand of the data-gradient GEMM
-    const int which = (MODE == MODE_R2) ? 2 : ((MODE == MODE_R3A || MODE == MODE_R3F) ? 1 : 0);
-    constexpr bool kResidual = MODE == MODE_R3B || MODE == MODE_R3F;      // output = dx of the block: add the skip gradient
-    constexpr bool kCnBackward = MODE == MODE_R3A || MODE == MODE_R3F;    // gradient image = context-norm backward of y1
+    const int which = (MODE == MODE_R2) ? 2 : 1;
+    constexpr bool kResidual = MODE == MODE_R3F;      // output = dx of the block: add the skip gradient
+    constexpr bool kCnBackward = MODE == MODE_R3F;    // gradient image = context-norm backward of y1
     const int mat = (net * L.depth + blk) * 3 + which;
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -239,7 +237,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                                   wsc.x, ch, tmem_base + lane_off + TMB_W_HI, tmem_base + lane_off + TMB_W_LO, cq & 1);
     // scale of the gradient image from the running maximum of what feeds it
     const float gin = a.gmax[gmax_slot(L.depth, net, blk, MODE == MODE_R3F ? 1 : MODE)];
-    const float gs = pow2_scale(gin, MODE == MODE_R3B ? 10 : 4);     // R2/R3A: |dy| <= ~1700 x the tracked maximum
+    const float gs = pow2_scale(gin, 4);                              // |dy| <= ~1700 x the tracked maximum
     const float un_d = wsc.y / gs;                                    // data-gradient accumulator -> FP32
     float* gout = a.gmax + (kResidual ? (blk > 0 ? gmax_slot(L.depth, net, blk - 1, 0) : gmax_slot(L.depth, net, L.depth, 0))
                                              : gmax_slot(L.depth, net, blk, MODE + 1));
@@ -261,7 +259,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
         const int valid = min(TE, E - tile * TE);
         const int64_t gobj = ((int64_t)net * L.N + obj) * CH * EP;
 
-        if (MODE != MODE_R3B && stat_obj != obj) {
+        if (stat_obj != obj) {
             if (tid < CH) {
                 st1_s[tid] = merge_cn_stats(stat_ptr(a.ws, L, net, blk, 0) + obj * (int64_t)T * CH, tid, T, E);
                 if (MODE == MODE_R2)
@@ -277,19 +275,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
         //      each lane one 256-bit load per array and one 16-byte chunk per image part
         {
             const float* S1p;   // first array feeding A1
-            const float* S2p;   // second array feeding A1 (R2: G, R3A: Y1)
+            const float* S2p;   // second array feeding A1 (R2: G, R3F: Y1)
             const float* S3p;   // array feeding A2
             if (MODE == MODE_R2) {
                 S1p = act_ptr(a.ws, L, net, blk, SLOT_Y2) + obj_off;
                 S2p = a.G + gobj;
                 S3p = act_ptr(a.ws, L, net, blk, SLOT_Y1) + obj_off;
-            } else if (kCnBackward) {
+            } else {
                 S1p = a.D1 + gobj;
                 S2p = act_ptr(a.ws, L, net, blk, SLOT_Y1) + obj_off;
-                S3p = act_ptr(a.ws, L, net, blk, MODE == MODE_R3F ? SLOT_X : SLOT_P) + obj_off;
-            } else {
-                S1p = a.DP + gobj;
-                S2p = nullptr;
                 S3p = act_ptr(a.ws, L, net, blk, SLOT_X) + obj_off;
             }
             const int64_t eoff = tile * TE + eblk * 8;
@@ -300,7 +294,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                 for (int u = 0; u < 2; ++u) {
                     const int c = warp * 8 + (it0 + u) * 2 + (lane >> 4);
                     b1[u] = ld256(S1p + (int64_t)c * EP + eoff);
-                    if (MODE != MODE_R3B) b2[u] = ld256(S2p + (int64_t)c * EP + eoff);
+                    b2[u] = ld256(S2p + (int64_t)c * EP + eoff);
                     b3[u] = ld256(S3p + (int64_t)c * EP + eoff);
                 }
 #pragma unroll
@@ -316,18 +310,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                             g[q] = s2.y * (dyh - sb.x - yh * sb.y);
                             h[q] = (b3[u].v[q] - s1.x) * s1.y;
                         }
-                    } else if (kCnBackward) {
+                    } else {
                         const float2 s1 = st1_s[c], sb = sb_s[c];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float yh = (b2[u].v[q] - s1.x) * s1.y;
                             g[q] = s1.y * (b1[u].v[q] - sb.x - yh * sb.y);
-                            h[q] = b3[u].v[q];
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            g[q] = b1[u].v[q];
                             h[q] = b3[u].v[q];
                         }
                     }
@@ -399,7 +387,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) mlp_bwd_tc_kernel(BwdTcArgs a, 
                 a.bstat[(((int64_t)net * 2 + 1) * L.N + obj) * T * CH + (int64_t)tile * CH + tid] =
                     make_float2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y));
             }
-            float* Out = (MODE == MODE_R2 ? a.D1 : (MODE == MODE_R3A ? a.DP : a.G)) + gobj + tile * TE;   // R3B, R3F: a.G
+            float* Out = (MODE == MODE_R2 ? a.D1 : a.G) + gobj + tile * TE;
 #pragma unroll 4
             for (int i = 0; i < 8; ++i) {
                 const int r = warp * 8 + i;
@@ -577,7 +565,7 @@ __global__ void __launch_bounds__(128) reduce_conv_in_tc_kernel(BwdTcArgs a, flo
 }
 
 struct BwdTcScratch {
-    int64_t G, D1, DP, bstat, wpart, inpart, gmax, dwf, total;   // float offsets
+    int64_t G, D1, bstat, wpart, inpart, gmax, dwf, total;   // float offsets
 };
 
 BwdTcScratch bwd_tc_layout(const WsLayout& L, int ctas) {
@@ -586,7 +574,6 @@ BwdTcScratch bwd_tc_layout(const WsLayout& L, int ctas) {
     auto take = [&](int64_t n) { int64_t r = o; o += (n + 63) & ~(int64_t)63; return r; };
     s.G = take(2 * L.act);
     s.D1 = take(2 * L.act);
-    s.DP = take(64);                                        // (gradient w.r.t. the preconv output: unused since the fold)
     s.bstat = take((int64_t)2 * 2 * L.stat * 2);
     s.wpart = take((int64_t)3 * 2 * ctas * CH * CH);
     s.inpart = take((int64_t)2 * L.N * L.T * CH * 8);
@@ -628,7 +615,6 @@ int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float
                                                (((size_t)a.L.total * sizeof(float) + 255) / 256) * 256);
     a.G = scratch + S.G;
     a.D1 = scratch + S.D1;
-    a.DP = scratch + S.DP;
     a.bstat = reinterpret_cast<float2*>(scratch + S.bstat);
     a.wpart = scratch + S.wpart;
     a.inpart = scratch + S.inpart;

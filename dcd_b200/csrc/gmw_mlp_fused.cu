@@ -758,23 +758,18 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
     uint32_t* wimg = reinterpret_cast<uint32_t*>(base + fused_scales_bytes(depth) + fused_bias_bytes(depth));
     float2* xg = reinterpret_cast<float2*>(base + fused_scales_bytes(depth) + fused_bias_bytes(depth) + fused_image_only_bytes(depth));
     // The CTAs of a group wait for each other, so all of them must be resident: cooperative launch, one CTA per SM.
-    static int max_groups_of[64] = {0};                       // per device (function attributes are per context)
+    // (queried on every call: the library keeps no state between calls; these are host-side lookups, no device work)
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return DCD_E_DEVICE;
-    if (max_groups_of[dev] == 0) {
-        cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
-        cudaFuncSetAttribute(fused_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CH * CH * sizeof(float)));
-        int coop = 0, per_sm = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_fused_kernel, FTHREADS, kFusedSmem);
-        if (!coop || per_sm < 1) return DCD_E_UNSUPPORTED;
-        int g = device_sm_count() * per_sm / FCS;
-        if (g > FMAX_GROUPS) g = FMAX_GROUPS;
-        if (g < 1) return DCD_E_UNSUPPORTED;
-        max_groups_of[dev] = g;
-    }
-    const int max_groups = max_groups_of[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess) return DCD_E_DEVICE;
+    cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+    cudaFuncSetAttribute(fused_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CH * CH * sizeof(float)));
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_fused_kernel, FTHREADS, kFusedSmem);
+    if (!coop || per_sm < 1) return DCD_E_UNSUPPORTED;
+    int max_groups = device_sm_count() * per_sm / FCS;
+    if (max_groups > FMAX_GROUPS) max_groups = FMAX_GROUPS;
+    if (max_groups < 1) return DCD_E_UNSUPPORTED;
     fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, a.fold, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
     const int64_t nitems = a.L.N * 2;

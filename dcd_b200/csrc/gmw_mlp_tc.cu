@@ -486,11 +486,8 @@ size_t tc_weight_image_bytes(int depth) { return tc_fold_offset_bytes(depth) + t
 
 // DCD_B200_LAYERWISE=1 forces the layer-wise kernels also for inference (A/B measurements, cross-checks)
 static bool force_layerwise() {
-    static const int v = [] {
-        const char* e = getenv("DCD_B200_LAYERWISE");
-        return (e != nullptr && e[0] == '1') ? 1 : 0;
-    }();
-    return v != 0;
+    const char* e = getenv("DCD_B200_LAYERWISE");           // read on every call: no cached library state
+    return e != nullptr && e[0] == '1';
 }
 
 int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,

@@ -29,7 +29,8 @@ def shard_bounds(counts: Sequence[int], world_size: int) -> List[Tuple[int, int]
     for r in range(world_size):
         lo = done
         target = (total * (r + 1) + world_size - 1) // world_size if r + 1 < world_size else total
-        while frame < len(counts) and (done < target):
+        last = r + 1 == world_size                 # the last rank also takes trailing frames without objects
+        while frame < len(counts) and (done < target or last):
             done += counts[frame]
             frame += 1
         bounds.append((lo, done))
@@ -62,7 +63,8 @@ def all_gather_depths(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], gr
 def allreduce_gradients(model, group=None, async_op: bool = False):
     """DDP-equivalent gradient averaging of the two parameter blobs of dcd_b200.ops.GMW.
 
-    One all-reduce per edge net (2.38 MB each), issued as soon as that net's gradient is final.
+    One all-reduce per edge net (2.38 MB each), called after backward() has produced both blobs
+    (at 4.76 MB the exchange costs < 0.1 ms on NVSwitch, so nothing is overlapped with the backward).
     Returns the work handles when async_op=True.
     """
     world = dist.get_world_size(group)

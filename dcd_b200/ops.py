@@ -37,6 +37,14 @@ def _num_edges(n: int) -> int:
     return n * (n - 1) // 2
 
 
+def _inference_only(name: str, *tensors) -> None:
+    """The frame-epilogue ops have no backward: fail loudly instead of silently cutting the
+    autograd graph when the reference would differentiate through them (detector_loss.py:391)."""
+    if torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError("dcd_b200.%s is inference-only (no backward is implemented): call it under torch.no_grad() "
+                           "or detach its inputs" % name)
+
+
 def _check_shapes(kps, kps_3d, rot, K=None):
     if kps.dim() != 3 or kps.shape[-1] != 2:
         raise ValueError("kps must be [N,n,2], got %s" % (tuple(kps.shape),))
@@ -221,8 +229,11 @@ def compute_pairs_kpts_depth(pred_extra_kpts_2d, pred_bbox_points, pred_offset_3
     keypoints `(kpts + (points + offsets)) * 4 - pad_size` are formed on the fly, solved over all keypoint pairs and
     averaged -> depth [N].  With `return_locations` also the object's 3D location (decode_location_flatten,
     anno_encoder.py:147-161, and `+ h / 2` on y when `dims` [N,3] is given, detector_infer.py:186-188) from the same launch.
-    P: the image's 3x4 projection matrix (or one per object), pad_size: [2], [1,2], or [B,2] with batch_idxs."""
+    P: the image's 3x4 projection matrix (or one per object), pad_size: [2], [1,2], or [B,2] with batch_idxs.
+    Inference-only (no backward; raises when an input requires grad)."""
     require_cuda(pred_extra_kpts_2d, pred_extra_kpts_3d, pred_rots, pred_bbox_points, pred_offset_3D)
+    _inference_only("compute_pairs_kpts_depth", pred_extra_kpts_2d, pred_extra_kpts_3d, pred_rots, pred_bbox_points,
+                    pred_offset_3D, dims)
     off, k3 = f32c(pred_extra_kpts_2d), f32c(pred_extra_kpts_3d)
     rot = f32c(pred_rots).reshape(-1)
     N, n = off.shape[0], off.shape[1]
@@ -245,8 +256,10 @@ def compute_pairs_kpts_depth(pred_extra_kpts_2d, pred_bbox_points, pred_offset_3
 
 def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=None):
     """Anno_Encoder.decode_location_flatten (DGDE/model/anno_encoder.py:147-161) with the calibration given as the
-    3x4 matrix of the image ([3,4]) or per object ([N,3,4]) instead of Calibration objects -> locations [N,3]."""
+    3x4 matrix of the image ([3,4]) or per object ([N,3,4]) instead of Calibration objects -> locations [N,3].
+    Inference-only (no backward; raises when an input requires grad)."""
     require_cuda(points, offsets, depths)
+    _inference_only("decode_location_flatten", points, offsets, depths)
     pts, ofs, dep = f32c(points), f32c(offsets), f32c(depths).reshape(-1)
     N, dev = pts.shape[0], pts.device
     K = _calib_per_object(P, N, dev)
@@ -261,8 +274,10 @@ def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=Non
 def select_point_of_interest(batch, index, feature_maps, validate: bool = False):
     """Drop-in for DGDE/model/layers/utils.py:120-145: feature_maps [B,C,H,W], index [B,K] flattened positions (or
     [B,K,2] (x, y) points) -> [B,K,C], reading only the selected values (no NHWC copy of the map).  An index outside the
-    map yields NaN; `validate=True` checks the range first (a host synchronisation) and raises like torch.gather."""
+    map yields NaN; `validate=True` checks the range first (a host synchronisation) and raises like torch.gather.
+    Inference-only (no backward; raises when feature_maps requires grad)."""
     require_cuda(feature_maps, index)
+    _inference_only("select_point_of_interest", feature_maps)
     fm = f32c(feature_maps)
     B, C, H, W = fm.shape
     if index.dim() == 3:
@@ -285,6 +300,7 @@ def decode_depth_from_keypoints_batch(pred_keypoints, pred_dimensions, P, batch_
     """Anno_Encoder.decode_depth_from_keypoints_batch (DGDE/model/anno_encoder.py:193-224) with the calibration as the
     image's 3x4 matrix ([3,4]; [B,3,4] with batch_idxs; or per object [N,3,4]) -> [N,3] (centre, corner_02, corner_13)."""
     require_cuda(pred_keypoints, pred_dimensions)
+    _inference_only("decode_depth_from_keypoints_batch", pred_keypoints, pred_dimensions)
     kp, dm = f32c(pred_keypoints).reshape(-1, 10, 2), f32c(pred_dimensions)
     N, dev = kp.shape[0], kp.device
     P = torch.as_tensor(P)
@@ -304,6 +320,8 @@ def depth_ensemble(pred_keypoints, pred_dimensions, P, keypoint_log_uncertainty,
     """Fused detector_infer.py:141-171,197-203: keypoint depths, uncertainties = exp(channels), inverse-uncertainty soft
     ensemble -> dict(keypoint_depths [N,3], depth [N], depth_error [N], min_uncertainty [N] int64, scores [N,1] or None)."""
     require_cuda(pred_keypoints, pred_dimensions, keypoint_log_uncertainty)
+    _inference_only("depth_ensemble", pred_keypoints, pred_dimensions, keypoint_log_uncertainty, direct_depths,
+                    direct_log_uncertainty, scores)
     kp, dm = f32c(pred_keypoints).reshape(-1, 10, 2), f32c(pred_dimensions)
     N, dev = kp.shape[0], kp.device
     K = _calib_per_object(P, N, dev)
@@ -332,6 +350,7 @@ def depth_ensemble(pred_keypoints, pred_dimensions, P, keypoint_log_uncertainty,
 def ray_rescale(raw_location, pred_depth, dim):
     """GMW/main.py:542-547: detector location [N,3] moved along its viewing ray to the GMW depth (dim [N,3] = (h,w,l))."""
     require_cuda(raw_location, pred_depth, dim)
+    _inference_only("ray_rescale", raw_location, pred_depth, dim)
     rl, pd, dm = f32c(raw_location), f32c(pred_depth).reshape(-1), f32c(dim)
     out = torch.empty_like(rl)
     if rl.shape[0]:
@@ -475,12 +494,13 @@ class GMW(nn.Module):
     SINKHORN_LAMBDA, SINKHORN_TOLERANCE, SINKHORN_ITERATIONS = 10.0, 1e-9, 100     # GMW/model/model.py:117-119
 
     @torch.no_grad()
-    def edge_transport(self, kpts_2d, kpts_3d, materialise: bool = True):
+    def edge_transport(self, kpts_2d, kpts_3d, materialise: bool = True, params=None):
         """Correspondence branch, forward only (GMW/model/model.py:170-192): returns
         (reg_weights [b,E], edge_P [b,E,E] or None, cls_terms [b,2] = (sum P, trace P)).
         correspondenceLoss(edge_P, eye) of GMW/main.py:456-457 is `(cls_terms[:, 0] - 2 * cls_terms[:, 1]).mean()`;
         with materialise=False the 4 E^2 bytes per object of edge_P are never written.  No gradient."""
-        require_cuda(kpts_2d, kpts_3d, self.params4)
+        p4, p6 = params if params is not None else (self.params4, self.params6)
+        require_cuda(kpts_2d, kpts_3d, p4, p6)
         k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
         N, n = k2.shape[0], k2.shape[1]
         E = _num_edges(n)
@@ -493,7 +513,7 @@ class GMW(nn.Module):
             f4 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
             f6 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
             ws = _alloc_bytes(L.dcd_gmw_workspace_bytes(N, n, self.depth, 0), dev)
-            check(L.dcd_gmw_weights_fwd(ptr(k2), ptr(k3), ptr(self.params4), ptr(self.params6), N, n, self.depth, 0,
+            check(L.dcd_gmw_weights_fwd(ptr(k2), ptr(k3), ptr(p4), ptr(p6), N, n, self.depth, 0,
                                         ptr(reg_w), ptr(f4), ptr(f6), ptr(ws), ws.numel() * 4, stream_ptr()), "dcd_gmw_weights_fwd")
             del ws
             tws = _alloc_bytes(L.dcd_gmw_transport_workspace_bytes(N, n), dev)
@@ -503,27 +523,42 @@ class GMW(nn.Module):
         return reg_w, P, sums
 
     def forward(self, kpts_2d, kpts_3d, pred_rot=None, args=None):
-        require_cuda(kpts_2d, kpts_3d, self.params4)
+        return self.forward_blobs(kpts_2d, kpts_3d, self.params4, self.params6)
+
+    def forward_blobs(self, kpts_2d, kpts_3d, params4, params6):
+        """forward() on explicit parameter blobs (dcd_b200.patch passes blobs packed from the LIVE reference parameters,
+        so that their optimizer, checkpoints and DDP hooks keep working unchanged)."""
+        require_cuda(kpts_2d, kpts_3d, params4, params6)
         k2, k3 = f32c(kpts_2d), f32c(kpts_3d)
         if k2.dim() != 3 or k2.shape[-1] != 2 or tuple(k3.shape) != (k2.shape[0], k2.shape[1], 3):
             raise ValueError("kpts_2d must be [b,n,2] and kpts_3d [b,n,3]")
-        need_grad = torch.is_grad_enabled() and (self.params4.requires_grad or self.params6.requires_grad)
+        need_grad = torch.is_grad_enabled() and (params4.requires_grad or params6.requires_grad)
         if self.with_edge_P and not need_grad:
-            reg_w, P, _ = self.edge_transport(k2, k3)
+            reg_w, P, _ = self.edge_transport(k2, k3, params=(params4, params6))
             return reg_w, P
-        reg_w = _GmwWeights.apply(k2, k3, self.params4, self.params6, self.depth, need_grad)
+        if self.with_edge_P:
+            raise NotImplementedError("dcd_b200.GMW: edge_P under autograd (the Sinkhorn backward) is not available in this build")
+        reg_w = _GmwWeights.apply(k2, k3, params4, params6, self.depth, need_grad)
         if _CHECK_FINITE and not bool(torch.isfinite(reg_w).all()):
             # the tensor-core path carries activations as FP16 hi+lo pairs: |activation| must stay below 65504
             raise FloatingPointError("dcd_b200.GMW: non-finite edge weights (activation outside the FP16 hi/lo range?)")
         return reg_w, None
 
 
-def compute_reg_loss(pre_depths, edge_weight, gt_depth, good_idx=None):
-    """Drop-in for GMW/main.py:364-371 -> (reg_loss, Z_select_weighted)."""
+def compute_reg_loss(pre_depths, edge_weight, gt_depth, good_idx=None, validate: bool = False):
+    """Drop-in for GMW/main.py:364-371 -> (reg_loss, Z_select_weighted).  Shapes are checked; `validate=True` also checks
+    the index range (a host synchronisation; the kernels clamp an out-of-range index instead of faulting)."""
     if good_idx is None:
         raise UnboundLocalError("compute_reg_loss needs good_idx (the reference fails without it too)")
     require_cuda(pre_depths, edge_weight, good_idx)
+    if edge_weight.dim() != 2 or tuple(pre_depths.shape) != tuple(edge_weight.shape):
+        raise RuntimeError("compute_reg_loss: pre_depths %s and edge_weight %s must both be [b,E]"
+                           % (tuple(pre_depths.shape), tuple(edge_weight.shape)))
+    if good_idx.dim() != 2 or good_idx.shape[0] != edge_weight.shape[0] or good_idx.shape[1] > edge_weight.shape[1]:
+        raise RuntimeError("compute_reg_loss: good_idx must be [b,k] with k <= E, got %s" % (tuple(good_idx.shape),))
     idx = good_idx.to(torch.int64).contiguous()
+    if validate and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= edge_weight.shape[1]):
+        raise RuntimeError("index out of range in compute_reg_loss (torch.gather raises here too)")
     Z = _GmwAggregate.apply(f32c(edge_weight), f32c(pre_depths), idx)
     reg_loss = (Z - gt_depth).abs().mean()
     return reg_loss, Z

@@ -6,8 +6,16 @@ plain method and `compute_z` / `compute_reg_loss` are module-level functions of 
 
     import dcd_b200.patch as patch
     patch.install(anno_encoder_cls=Anno_Encoder)                       # DGDE (train + inference)
-    patch.install(gmw_main=main_module, gmw_model=model.module)        # GMW  (train + validation)
+    patch.install(gmw_main=main_module, gmw_model=model)               # GMW  (train + validation)
     patch.uninstall()
+
+GMW parameters stay where the reference keeps them: the patched `forward` packs the LIVE `nn.Parameter`s of the
+reference module into the kernels' two flat blobs with one differentiable `torch.cat` per call, so
+  * `optimizer.step()`, `load_state_dict` (`--resume`, GMW/main.py:275-297), `.to()` and DDP's gradient hooks act on the
+    tensors the kernels read next — no snapshot that could go stale;
+  * `loss.backward()` leaves the gradients in the reference parameters' `.grad` (autograd walks back through the
+    cat), so `optimizer.zero_grad()` / `optimizer.step()` of GMW/main.py:463-466 work unchanged and nothing accumulates
+    behind their back.
 """
 from __future__ import annotations
 
@@ -17,6 +25,7 @@ from typing import List, Tuple
 import torch
 
 from . import ops
+from .weights import NET_NAMES, pack_parameters
 
 _undo: List[Tuple[object, str, object, bool]] = []
 
@@ -35,13 +44,44 @@ def _decode_method(self, kps, kps_3d, rot_y, K, training=False, kpts_2d_mask=Non
                                        gt_depth=gt_depth, weight=weight)
 
 
-def install(anno_encoder_cls=None, gmw_main=None, gmw_model=None) -> None:
+class _LiveBlobs:
+    """Parameter blobs of a reference GMW module, re-packed from its live parameters.
+
+    Under autograd every call packs afresh (the cat is what routes the gradients); without autograd the packed
+    blobs are cached and re-used until any parameter's version counter or storage changes (optimizer step,
+    load_state_dict, .to())."""
+
+    def __init__(self, gmw_model, depth: int):
+        self.model = gmw_model
+        self.depth = depth
+        self._key = None
+        self._blobs = None
+
+    def _params(self):
+        return {k: p for k, p in self.model.named_parameters()}
+
+    def get(self):
+        params = self._params()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params.values())
+        if need_grad:
+            return tuple(pack_parameters(params, name, cin, self.depth) for name, cin in NET_NAMES)
+        key = tuple((k, p.data_ptr(), p._version) for k, p in params.items())
+        if key != self._key:
+            with torch.no_grad():
+                self._blobs = tuple(pack_parameters(params, name, cin, self.depth) for name, cin in NET_NAMES)
+            self._key = key
+        return self._blobs
+
+
+def install(anno_encoder_cls=None, gmw_main=None, gmw_model=None, with_edge_P: bool = True) -> None:
     """Patch whichever reference objects are given.
 
     anno_encoder_cls: the reference `Anno_Encoder` class (or an instance).
     gmw_main:         the imported GMW/main.py module (compute_z, compute_reg_loss are replaced).
-    gmw_model:        a reference `GMW` nn.Module instance; its weights are copied into a
-                      dcd_b200.ops.GMW and its forward is redirected (edge_P is returned as None).
+    gmw_model:        a reference `GMW` nn.Module instance (the bare module, not its DDP wrapper); its `forward` is
+                      redirected to the kernels, reading the module's own parameters on every call.
+    with_edge_P:      return the Sinkhorn correspondence matrix `edge_P` like the reference (both loops of GMW/main.py
+                      dereference it, :456 and :526); False returns None in its place and skips that branch.
     """
     if anno_encoder_cls is not None:
         target = anno_encoder_cls
@@ -51,12 +91,18 @@ def install(anno_encoder_cls=None, gmw_main=None, gmw_model=None) -> None:
         _set(gmw_main, "compute_z", ops.compute_z)
         _set(gmw_main, "compute_reg_loss", ops.compute_reg_loss)
     if gmw_model is not None:
-        dev = next(gmw_model.parameters()).device
-        fast = ops.GMW().to(dev).load_reference_state_dict(gmw_model.state_dict())
+        if not hasattr(gmw_model, "FeatureExtractor4d"):
+            raise TypeError("install(gmw_model=...) needs the bare reference GMW module (pass model.module for a DDP wrapper)")
+        depth = sum(1 for k, _ in gmw_model.FeatureExtractor4d.named_children() if k.startswith("conv_") and k != "conv_in")
+        fast = ops.GMW(depth=depth)            # its own parameters are not used: the blobs come from the live reference module
+        fast.with_edge_P = bool(with_edge_P)
+        live = _LiveBlobs(gmw_model, fast.depth)
         _set(gmw_model, "_dcd_b200", fast)
+        _set(gmw_model, "_dcd_b200_blobs", live)
 
-        def forward(kpts_2d, kpts_3d, pred_rot=None, args=None, _fast=fast):
-            return _fast(kpts_2d, kpts_3d, pred_rot, args)
+        def forward(kpts_2d, kpts_3d, pred_rot=None, args=None, _fast=fast, _live=live):
+            p4, p6 = _live.get()
+            return _fast.forward_blobs(kpts_2d, kpts_3d, p4, p6)
 
         _set(gmw_model, "forward", forward)
 
@@ -74,10 +120,6 @@ def uninstall() -> None:
 
 
 def sync_gradients_to_reference(gmw_model) -> None:
-    """Copy the blob gradients of the patched model into the reference module's .grad fields so
-    that the reference's optimizer (GMW/main.py:255,466) keeps working unchanged."""
-    fast = gmw_model._dcd_b200
-    grads = fast.reference_grads()
-    with torch.no_grad():
-        for k, p in gmw_model.named_parameters():
-            p.grad = grads[k].reshape(p.shape).clone()
+    """Kept for callers written against the first release: the gradients already live in the reference parameters'
+    `.grad` (see the module docstring), so there is nothing to copy."""
+    return None

@@ -44,6 +44,17 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], prefix: str, cin: int, depth: i
     return blob
 
 
+def pack_parameters(params: Dict[str, torch.Tensor], prefix: str, cin: int, depth: int = NET_DEPTH) -> torch.Tensor:
+    """Differentiable form of pack_state_dict: `params` maps the reference names to the LIVE parameters
+    (dict(model.named_parameters())); the blob is one torch.cat, so autograd carries the blob gradient back to
+    every reference parameter's .grad (transposes and splits) without any bookkeeping by the caller."""
+    parts = []
+    for stem, _, _, fin in _entries(prefix, cin, depth):
+        parts.append(params[stem + ".0.weight"].to(torch.float32).reshape(NET_CH, fin).t().reshape(-1))
+        parts.append(params[stem + ".0.bias"].to(torch.float32).reshape(-1))
+    return torch.cat(parts)
+
+
 def unpack_blob(blob: torch.Tensor, prefix: str, cin: int, depth: int = NET_DEPTH) -> Dict[str, torch.Tensor]:
     """Flat blob (parameters or gradients) -> tensors named and shaped like the reference state_dict."""
     out = {}

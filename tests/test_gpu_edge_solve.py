@@ -232,3 +232,85 @@ def test_full_kitti_val_batch_solve():
     assert torch.equal(d_s, d_o)
     assert rel_err(mean[lo:lo + 512], d_o.mean(1)) < 1e-6
     assert bool(torch.isfinite(mean).all())
+
+
+@pytest.mark.parametrize("n,N", [(73, 5000), (60, 4000), (256, 2400), (10, 4000), (128, 2500), (100, 3001), (2, 3000), (3, 2999)])
+def test_group_mean_kernel_matches_per_edge_mean(n, N):
+    """The throughput mean kernel (groups of objects per warp, circulant pair enumeration, packed FP32 pairs) against the
+    mean of the per-edge depths (bit-exact vs the oracle) for odd / even / tiny / maximal keypoint counts; per-object
+    results must not depend on where an object falls in its group (permutation, ragged tail)."""
+    ob = synth.make_objects(N=N, n=n, seed=300 + n)
+    kps, k3, rot, K = cu(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
+    mean = dcd_b200.edge_depth_mean(kps, k3, rot, K)
+    d, _ = dcd_b200.decode_pairs_kpts_depth(kps[:1000], k3[:1000], rot[:1000], K[:1000])
+    ref64 = d.double().mean(1)
+    assert rel_err(mean[:1000], ref64) < 1e-6
+    d_o, _ = O.decode_pairs_kpts_depth(kps[:200], k3[:200], rot[:200], K[:200])
+    assert torch.equal(d[:200], d_o)
+    # the same objects at other positions of their groups: bit-identical
+    sh = 3
+    m2 = dcd_b200.edge_depth_mean(kps[sh:], k3[sh:], rot[sh:], K[sh:])
+    assert torch.equal(m2, mean[sh:])
+    # GMW form (no calibration, other clamp) through the same kernel
+    lo, hi = 0.1, 80.0
+    from dcd_b200 import _lib
+    from dcd_b200._lib import check, ptr, stream_ptr
+    out = torch.empty(N, device=DEV)
+    k2n = ob.kps_norm.to(DEV)
+    check(_lib.lib().dcd_edge_solve_fwd(ptr(k2n), ptr(k3), ptr(rot.reshape(-1).contiguous()), 0, N, n, lo, hi, 0, 0, ptr(out),
+                                        stream_ptr()), "solve")
+    Zo, _ = O.compute_z(k2n[:300], k3[:300], rot[:300]) if n * (n - 1) // 2 >= 1500 else (None, None)
+    if Zo is not None:
+        assert rel_err(out[:300], Zo.double().mean(1)) < 1e-6
+
+
+def test_non_finite_inputs_follow_torch_clamp_semantics():
+    """torch.clamp propagates NaN (anno_encoder.py:371,375) and inf/inf is NaN; fminf/fmaxf alone would swallow them."""
+    N, n = 3000, 73
+    ob = synth.make_objects(N=N, n=n, seed=91)
+    kps, k3 = ob.kps.clone(), ob.kps_3d.clone()
+    kps[0, 5, 1] = float("nan")
+    k3[1, 7, 1] = float("inf")
+    k3[2, 3, 0] = float("nan")
+    kps[4, 1, 1] = float("inf")
+    kps[4, 2, 1] = float("inf")
+    k3[5, 9, 1] = float("inf")
+    k3[5, 11, 1] = float("-inf")
+    kps[2999, 72, 1] = float("nan")
+    kps, k3, rot, K = cu(kps, k3, ob.rot_y, ob.K)
+    d, _ = dcd_b200.decode_pairs_kpts_depth(kps, k3, rot, K)
+    bad = [0, 1, 2, 4, 5, 2999]
+    d_o, _ = O.decode_pairs_kpts_depth(kps[bad], k3[bad], rot[bad], K[bad])
+    assert torch.equal(torch.isnan(d[bad]), torch.isnan(d_o))
+    assert torch.equal(torch.nan_to_num(d[bad], nan=-1.0), torch.nan_to_num(d_o, nan=-1.0))
+    assert bool(torch.isnan(d[0]).any()) and not bool(torch.isnan(d[3]).any())
+    # small batch (CTA-per-object kernel) and fused mean (group kernel): NaN where the reference's mean is NaN
+    d_s, _ = dcd_b200.decode_pairs_kpts_depth(kps[:8], k3[:8], rot[:8], K[:8])
+    assert torch.equal(torch.nan_to_num(d_s, nan=-1.0), torch.nan_to_num(d[:8], nan=-1.0))
+    mean = dcd_b200.edge_depth_mean(kps, k3, rot, K)
+    ref_nan = torch.isnan(d.mean(1))
+    assert torch.equal(torch.isnan(mean), ref_nan)
+    ok = ~ref_nan
+    assert rel_err(mean[ok], d.double().mean(1)[ok]) < 1e-6
+    # compute_z form and the selection: NaN keys sort first, as in torch.topk
+    Z, idx = dcd_b200.compute_z(kps[:8], k3[:8], rot[:8])
+    Zo, idxo = O.compute_z(kps[:8], k3[:8], rot[:8])
+    assert torch.equal(torch.nan_to_num(Z, nan=-1.0), torch.nan_to_num(Zo, nan=-1.0))
+    good = [3, 6, 7]
+    assert torch.equal(idx[good], idxo[good])
+
+
+@pytest.mark.parametrize("n,N,k", [(73, 3000, 1500), (256, 300, 1500), (60, 500, 1500), (73, 64, 2048), (73, 33, 7), (100, 40, 2500)])
+def test_radix_select_matches_oracle_topk(n, N, k):
+    """edge_select (radix select + register bitonic sort for k <= 2048, shared-memory sort above) against the oracle's
+    canonical top-k on CUDA, incl. quantised inputs with many tied keys straddling rank k."""
+    ob = synth.make_objects(N=N, n=n, seed=500 + n + k)
+    k2 = ob.kps_norm.clone()
+    k2[: N // 2, :, 1] = torch.round(k2[: N // 2, :, 1] * 40) / 40           # many duplicate |V|
+    k2[0, :, 1] = 0.125                                                       # all keys equal
+    k2d, k3, rot = cu(k2, ob.kps_3d, ob.rot_y)
+    Z, idx = dcd_b200.compute_z(k2d, k3, rot, num_k=k)
+    Zo, idxo = O.compute_z(k2d, k3, rot, num_k=k)
+    assert torch.equal(idx, idxo)
+    assert torch.equal(Z, Zo)
+    assert torch.equal(idx[0].cpu(), torch.arange(k))

@@ -150,6 +150,12 @@ def test_shard_bounds_cover_and_balance():
             cuts.add(cum)
         assert all(lo in cuts and hi in cuts for lo, hi in b)   # shards end on frame boundaries
     assert ddist.shard_bounds([5], 4) == [(0, 5), (5, 5), (5, 5), (5, 5)]
+    # frames without detections (common in KITTI), also trailing ones
+    assert ddist.shard_bounds([3, 0], 1) == [(0, 3)]
+    assert ddist.shard_bounds([3, 2, 0], 2) == [(0, 3), (3, 5)]
+    assert ddist.shard_bounds([0, 0], 2) == [(0, 0), (0, 0)]
+    assert ddist.shard_bounds([0, 3, 0, 0, 2, 0], 3) == [(0, 3), (3, 5), (5, 5)]
+    assert ddist.shard_bounds([], 2) == [(0, 0), (0, 0)]
 
 
 def test_patch_install_and_uninstall():
@@ -197,10 +203,39 @@ def test_patch_against_the_real_reference_objects():
     try:
         assert ref_main.compute_z is dcd_b200.compute_z
         assert len(model.state_dict()) == n_keys                     # the fast module is not registered as a sub-module
-        fast = model._dcd_b200
-        back = fast.reference_state_dict()
-        for k, v in model.state_dict().items():
-            assert torch.equal(back[k], v), k
+        assert model._dcd_b200.depth == 12 and model._dcd_b200.with_edge_P
+        live = model._dcd_b200_blobs
+        with torch.no_grad():
+            p4, p6 = live.get()
+        for (name, cin), blob in zip(weights.NET_NAMES, (p4, p6)):
+            back = weights.unpack_blob(blob, name, cin)
+            for k, v in back.items():
+                assert torch.equal(v, model.state_dict()[k]), k
+        # the blobs follow the live parameters: an optimizer step or a load_state_dict is seen by the next forward
+        with torch.no_grad():
+            assert live.get()[0] is p4                                   # cached while nothing changed
+            first = next(model.parameters())
+            first.add_(1.0)
+            q4, _ = live.get()
+            assert q4 is not p4 and not torch.equal(q4, p4)
+            sd2 = {k: v + 0.5 for k, v in model.state_dict().items()}
+            model.load_state_dict(sd2)
+            r4, r6 = live.get()
+            for (name, cin), blob in zip(weights.NET_NAMES, (r4, r6)):
+                for k, v in weights.unpack_blob(blob, name, cin).items():
+                    assert torch.equal(v, sd2[k]), k
+        # under autograd the pack is differentiable: blob gradients land in the reference parameters' .grad
+        b4, b6 = live.get()
+        assert b4.requires_grad and b6.requires_grad
+        g = torch.Generator().manual_seed(0)
+        c4, c6 = torch.randn(b4.shape, generator=g), torch.randn(b6.shape, generator=g)
+        ((b4 * c4).sum() + (b6 * c6).sum()).backward()
+        for (name, cin), coef in zip(weights.NET_NAMES, (c4, c6)):
+            expect = weights.unpack_blob(coef, name, cin)
+            for k, p in model.named_parameters():
+                if k.startswith(name):
+                    assert torch.equal(p.grad, expect[k]), k
+        model.zero_grad()
         ob = synth.make_objects(N=2, n=73, seed=2)
         with pytest.raises(RuntimeError, match="CUDA"):
             enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)
@@ -209,6 +244,6 @@ def test_patch_against_the_real_reference_objects():
     finally:
         patch.uninstall()
     assert type(enc).decode_pairs_kpts_depth is orig_decode and ref_main.compute_z is orig_cz
-    assert model.forward == orig_forward and not hasattr(model, "_dcd_b200")
+    assert model.forward == orig_forward and not hasattr(model, "_dcd_b200") and not hasattr(model, "_dcd_b200_blobs")
     d, _ = enc.decode_pairs_kpts_depth(ob.kps, ob.kps_3d, ob.rot_y, ob.K)        # the reference path works again
     assert d.shape == (2, 2628)
