@@ -548,6 +548,8 @@ def kitti_val_stages(ctx, ob, d_k2, d_k3, d_rot, model):
     st = stream_ptr()
     ms_mean = time_kernel(lambda: check(L.dcd_edge_solve_fwd(ptr(d_kps), ptr(d_k3), ptr(d_rot), ptr(d_K), N, N_KPTS, 2.0, 80.0, 3,
                                                              0, ptr(mean), st), "solve"))
+    ms_fast = time_kernel(lambda: check(L.dcd_edge_solve_fwd(ptr(d_kps), ptr(d_k3), ptr(d_rot), ptr(d_K), N, N_KPTS, 2.0, 80.0, 3 | 4,
+                                                             0, ptr(mean), st), "solve"))
     ms_edges = time_kernel(lambda: check(L.dcd_edge_solve_fwd(ptr(d_kps), ptr(d_k3), ptr(d_rot), ptr(d_K), N, N_KPTS, 2.0, 80.0, 3,
                                                               ptr(edges), 0, st), "solve"))
     del edges
@@ -637,6 +639,10 @@ def kitti_val_stages(ctx, ob, d_k2, d_k3, d_rot, model):
                             "issue_slot_ceiling": "12 issue slots per edge in the SASS of the inner loop (3 LDS + 5.5 packed FP32 + "
                                                   "3 FMNMX + 1 MUFU, minus rounding) for 11 counted FLOP: at most 11 / (2 x 12) = 46 % "
                                                   "of the FP32-FMA roofline"},
+        "dgde_solve_mean_fast": {"objects_per_s": N / (ms_fast * 1e-3), "ms": ms_fast,
+                                 "fp32_tflops": F_SOLVE * N / (ms_fast * 1e-3) / 1e12,
+                                 "what": "opt-in DCD_FAST_QUOTIENT: hardware reciprocal instead of the IEEE division (per-object depth within "
+                                         "1e-6 of the default; per-edge values not bit-faithful)"},
         "dgde_solve_edges": {"objects_per_s": N / (ms_edges * 1e-3), "ms": ms_edges,
                              "hbm_gbs": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9,
                              "frac_hbm": (B_SOLVE + 4 * EDGES) * N / (ms_edges * 1e-3) / 1e9 / peaks["hbm_gbs"]},

@@ -33,7 +33,9 @@ SIGNATURES = {
     "dcd_gmw_transport_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dcd_gmw_transport_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int] + [c_void_p] * 5 + [c_size_t, c_void_p]),
     "dcd_gmw_bwd_scratch_bytes": (c_size_t, [c_int64, c_int, c_int]),
-    "dcd_gmw_weights_bwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int] + [c_void_p] * 4 + [c_size_t, c_void_p, c_size_t, c_void_p]),
+    "dcd_gmw_transport_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "dcd_gmw_transport_bwd": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_int, c_float] + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "dcd_gmw_weights_bwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int] + [c_void_p] * 6 + [c_size_t, c_void_p, c_size_t, c_void_p]),
     "dcd_gmw_aggregate_fwd": (c_int, [c_void_p] * 3 + [c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dcd_gmw_aggregate_bwd": (c_int, [c_void_p] * 3 + [c_int64, c_int64, c_int, c_int] + [c_void_p] * 4),
     "dcd_gmw_depth_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int64]),
@@ -55,7 +57,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dcd_version() != 1:
+    if lib.dcd_version() != 2:
         raise RuntimeError("libdcd_b200.so ABI version mismatch")
     return lib
 

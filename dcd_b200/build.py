@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcd_b200.so")
-SOURCES = ["abi.cu", "edge_solve.cu", "edge_select.cu", "dgde_locate.cu", "gmw_aggregate.cu", "gmw_transport.cu", "gmw_mlp_tc.cu", "gmw_mlp_fused.cu", "gmw_mlp_bwd_tc.cu"]
+SOURCES = ["abi.cu", "edge_solve.cu", "edge_select.cu", "dgde_locate.cu", "gmw_aggregate.cu", "gmw_transport.cu", "gmw_transport_bwd.cu", "gmw_mlp_tc.cu", "gmw_mlp_fused.cu", "gmw_mlp_bwd_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

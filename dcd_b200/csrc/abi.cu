@@ -27,7 +27,10 @@ int launch_gmw_transport_fwd(const float*, const float*, int64_t, int, float, fl
 size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth);
 size_t tc_weight_image_bytes(int depth);
 int launch_gmw_weights_bwd(const float*, const float*, const float*, const float*, int64_t, int, int, const float*,
-                           float*, float*, float*, float*, cudaStream_t);
+                           const float*, const float*, float*, float*, float*, float*, cudaStream_t);
+size_t gmw_transport_bwd_workspace_bytes(int64_t N, int E);
+int launch_gmw_transport_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int64_t, int, float,
+                             int, float, float*, float*, float*, void*, cudaStream_t);
 }  // namespace dcd
 
 using namespace dcd;
@@ -155,6 +158,25 @@ int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int
                                     (cudaStream_t)stream);
 }
 
+size_t dcd_gmw_transport_bwd_workspace_bytes(int64_t N, int n) {
+    if (N <= 0 || bad_n(n)) return 0;
+    return gmw_transport_bwd_workspace_bytes(N, (int)num_edges(n));
+}
+
+int dcd_gmw_transport_bwd(const float* feat4, const float* feat6, const float* P, const float* u, const float* v,
+                          const float* grad_P, int64_t N, int n, float lambda, int max_cg_iterations, float cg_tolerance,
+                          float* grad_nfeat4, float* grad_nfeat6, float* cg_info, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (N < 0 || bad_n(n) || max_cg_iterations < 1 || !(lambda > 0.f) || !(cg_tolerance >= 0.f)) return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!feat4 || !feat6 || !P || !u || !v || !grad_P || !grad_nfeat4 || !grad_nfeat6) return DCD_E_INVALID;
+    if (N > 65535) return DCD_E_UNSUPPORTED;
+    if (misaligned(P, 16) || misaligned(grad_P, 16)) return DCD_E_INVALID;
+    if (misaligned(workspace, 256) || workspace_bytes < dcd_gmw_transport_bwd_workspace_bytes(N, n)) return DCD_E_WORKSPACE;
+    return launch_gmw_transport_bwd(feat4, feat6, P, u, v, grad_P, N, (int)num_edges(n), lambda, max_cg_iterations, cg_tolerance,
+                                    grad_nfeat4, grad_nfeat6, cg_info, workspace, (cudaStream_t)stream);
+}
+
 size_t dcd_gmw_param_count(int cin, int depth) { return (size_t)blob_size(cin, depth); }
 
 size_t dcd_gmw_workspace_bytes(int64_t N, int n, int depth, int save) {
@@ -181,17 +203,18 @@ size_t dcd_gmw_bwd_scratch_bytes(int64_t N, int n, int depth) {
 }
 
 int dcd_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
-                        int64_t N, int n, int depth, const float* grad_reg_weights, float* grad_params4,
+                        int64_t N, int n, int depth, const float* grad_reg_weights, const float* grad_nfeat4,
+                        const float* grad_nfeat6, float* grad_params4,
                         float* grad_params6, void* workspace, size_t workspace_bytes, void* scratch,
                         size_t scratch_bytes, void* stream) {
     if (N <= 0 || bad_n(n) || depth < 1) return DCD_E_INVALID;
-    if (!kpts2d || !kpts3d || !params4 || !params6 || !grad_reg_weights || !grad_params4 || !grad_params6)
-        return DCD_E_INVALID;
+    if (!kpts2d || !kpts3d || !params4 || !params6 || !grad_params4 || !grad_params6) return DCD_E_INVALID;
+    if (!grad_reg_weights && !grad_nfeat4 && !grad_nfeat6) return DCD_E_INVALID;
     if (!workspace || !scratch) return DCD_E_INVALID;
     if (misaligned(workspace, 256) || workspace_bytes < dcd_gmw_workspace_bytes(N, n, depth, 1)) return DCD_E_WORKSPACE;
     if (misaligned(scratch, 256) || scratch_bytes < dcd_gmw_bwd_scratch_bytes(N, n, depth)) return DCD_E_WORKSPACE;
-    return launch_gmw_weights_bwd(kpts2d, kpts3d, params4, params6, N, n, depth, grad_reg_weights, grad_params4,
-                                  grad_params6, static_cast<float*>(workspace), static_cast<float*>(scratch),
+    return launch_gmw_weights_bwd(kpts2d, kpts3d, params4, params6, N, n, depth, grad_reg_weights, grad_nfeat4, grad_nfeat6,
+                                  grad_params4, grad_params6, static_cast<float*>(workspace), static_cast<float*>(scratch),
                                   (cudaStream_t)stream);
 }
 

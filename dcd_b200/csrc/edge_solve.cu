@@ -266,9 +266,9 @@ edge_solve_fwd_warp_kernel(const float* __restrict__ kps, const float* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int GRP_WARPS = 4;
 __host__ __device__ constexpr int grp_stride(int n) { return n + 32 * ((n / 2 + 31) / 32); }   // == n (mod 32), >= n + n/2
-__host__ __device__ constexpr int grp_warp_floats(int n, int G) { return 3 * G * grp_stride(n) + ((G * n + 31) & ~31) + 8 * G; }
+__host__ __device__ constexpr int grp_warp_floats(int n, int G) { return 3 * G * grp_stride(n) + ((G * n + 31) & ~31) + 8 * G; }   // v, Y, vC | per-slot sums | 5 per-object scalars
 
-template <int NK, int GC>
+template <int NK, int GC, bool FAST>
 __global__ void __launch_bounds__(GRP_WARPS * 32)
 edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
                        const float* __restrict__ rot, const float* __restrict__ K,
@@ -286,8 +286,7 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
     float* Y_s = v_s + G * S;
     float* c_s = Y_s + G * S;
     float* part_s = c_s + G * S;                             // [G * n] per-slot sums
-    float4* sc_s = reinterpret_cast<float4*>(part_s + ((G * n + 31) & ~31));    // [G] (sin, cos, cy, fy)
-    float* b3_s = reinterpret_cast<float*>(sc_s + G);        // [G]
+    float* sc_s = part_s + ((G * n + 31) & ~31);             // [5][G]: sin, cos, cy, fy, b3 of the group's objects
     const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
     const int64_t ngroups = (N + G - 1) / G;
 
@@ -304,8 +303,11 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
                 if (flags & DCD_SUB_B3) b3 = __ldg(Ko + 11);
             }
             const float r = __ldg(rot + obj);
-            sc_s[lane] = make_float4(sinf(r), cosf(r), cy, fy);
-            b3_s[lane] = b3;
+            sc_s[lane] = sinf(r);
+            sc_s[G + lane] = cosf(r);
+            sc_s[2 * G + lane] = cy;
+            sc_s[3 * G + lane] = fy;
+            sc_s[4 * G + lane] = b3;
         }
         __syncwarp();
         // ---- stage the group's keypoint terms: global keypoint index = obj0 * n + slot (coalesced)
@@ -317,9 +319,8 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
             const int s = s0 + lane;
             if (s < slots) {
                 const int g = s / n, i = s - g * n;
-                const float4 q = sc_s[g];
                 const float4 t = keypoint_terms(__ldg(kv + 2 * s), __ldg(k3 + 3 * s), __ldg(k3 + 3 * s + 1), __ldg(k3 + 3 * s + 2),
-                                                q.x, q.y, normalise, q.z, q.w);
+                                                sc_s[g], sc_s[G + g], normalise, sc_s[2 * G + g], sc_s[3 * G + g]);
                 const int base = g * S + i;
                 v_s[base] = t.x; Y_s[base] = t.y; c_s[base] = t.z;
                 if (i < D) { v_s[base + n] = t.x; Y_s[base + n] = t.y; c_s[base + n] = t.z; }
@@ -345,19 +346,25 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
                 int d = 1;
                 if (NK > 0) {
 #pragma unroll
-                    for (; d + 1 <= Dfull; d += 2)
-                        acc = add2_rn(acc, edge_quotient_finite2(vi2, Yi2, ci2, make_float2(pv[d], pv[d + 1]), make_float2(pY[d], pY[d + 1]),
-                                                                 make_float2(pc[d], pc[d + 1]), lo, hi));
+                    for (; d + 1 <= Dfull; d += 2) {
+                        const float2 vj = make_float2(pv[d], pv[d + 1]), Yj = make_float2(pY[d], pY[d + 1]), cj = make_float2(pc[d], pc[d + 1]);
+                        acc = add2_rn(acc, FAST ? edge_quotient_fast2(vi2, Yi2, ci2, vj, Yj, cj, lo, hi)
+                                                : edge_quotient_finite2(vi2, Yi2, ci2, vj, Yj, cj, lo, hi));
+                    }
                 } else {
 #pragma unroll 2
-                    for (; d + 1 <= Dfull; d += 2)
-                        acc = add2_rn(acc, edge_quotient_finite2(vi2, Yi2, ci2, make_float2(pv[d], pv[d + 1]), make_float2(pY[d], pY[d + 1]),
-                                                                 make_float2(pc[d], pc[d + 1]), lo, hi));
+                    for (; d + 1 <= Dfull; d += 2) {
+                        const float2 vj = make_float2(pv[d], pv[d + 1]), Yj = make_float2(pY[d], pY[d + 1]), cj = make_float2(pc[d], pc[d + 1]);
+                        acc = add2_rn(acc, FAST ? edge_quotient_fast2(vi2, Yi2, ci2, vj, Yj, cj, lo, hi)
+                                                : edge_quotient_finite2(vi2, Yi2, ci2, vj, Yj, cj, lo, hi));
+                    }
                 }
                 acc0 = acc.x;
                 acc1 = acc.y;
-                if (d <= Dfull) acc0 += edge_quotient_finite(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi);
-                if (D > Dfull && i < D) acc1 += edge_quotient_finite(vi, Yi, ci, pv[D], pY[D], pc[D], lo, hi);
+                if (d <= Dfull) acc0 += FAST ? edge_quotient_fast(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi)
+                                             : edge_quotient_finite(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi);
+                if (D > Dfull && i < D) acc1 += FAST ? edge_quotient_fast(vi, Yi, ci, pv[D], pY[D], pc[D], lo, hi)
+                                                     : edge_quotient_finite(vi, Yi, ci, pv[D], pY[D], pc[D], lo, hi);
             } else {
 #pragma unroll 1
                 for (int d = 1; d <= Dfull; ++d) acc0 += edge_quotient_ieee(vi, Yi, ci, pv[d], pY[d], pc[d], lo, hi);
@@ -371,7 +378,7 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
             float t = 0.f;
             for (int i = lane; i < n; i += 32) t += part_s[g * n + i];
             t = warp_sum(t);
-            if (lane == 0) depth_mean[obj0 + g] = __fsub_rn(__fdiv_rn(t, (float)E), b3_s[g]);
+            if (lane == 0) depth_mean[obj0 + g] = __fsub_rn(__fdiv_rn(t, (float)E), sc_s[4 * G + g]);
         }
         __syncwarp();                                        // all lanes done with the group's arrays before restaging
     }
@@ -588,15 +595,20 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
         if (per_sm < 1) return DCD_E_UNSUPPORTED;
         const int64_t cap = (int64_t)sms * per_sm;
         const int grid = (int)(want < cap ? want : cap);
+        const bool fast = (flags & DCD_FAST_QUOTIENT) != 0;
+#define DCD_LAUNCH_GRP(NKV, GCV, FASTV)                                                                                       \
+    do {                                                                                                                      \
+        if (gsmem > 48 * 1024)                                                                                                \
+            cudaFuncSetAttribute(edge_mean_group_kernel<NKV, GCV, FASTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem); \
+        edge_mean_group_kernel<NKV, GCV, FASTV><<<grid, GRP_WARPS * 32, gsmem, st>>>(kps, kps3d, rot, K, N, n, G, lo, hi, flags, \
+                                                                                      depth_mean);                           \
+    } while (0)
         if (n == 73) {
-            if (gsmem > 48 * 1024)
-                cudaFuncSetAttribute(edge_mean_group_kernel<73, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-            edge_mean_group_kernel<73, 7><<<grid, GRP_WARPS * 32, gsmem, st>>>(kps, kps3d, rot, K, N, n, G, lo, hi, flags, depth_mean);
+            if (fast) DCD_LAUNCH_GRP(73, 7, true); else DCD_LAUNCH_GRP(73, 7, false);
         } else {
-            if (gsmem > 48 * 1024)
-                cudaFuncSetAttribute(edge_mean_group_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-            edge_mean_group_kernel<0, 0><<<grid, GRP_WARPS * 32, gsmem, st>>>(kps, kps3d, rot, K, N, n, G, lo, hi, flags, depth_mean);
+            if (fast) DCD_LAUNCH_GRP(0, 0, true); else DCD_LAUNCH_GRP(0, 0, false);
         }
+#undef DCD_LAUNCH_GRP
         DCD_CHECK_LAUNCH();
         return DCD_OK;
     }

@@ -89,8 +89,10 @@ __global__ void bwd_tc_init_kernel(float* gmax, int n) {
     if (i < n) gmax[i] = 0.f;
 }
 
-// BW0: d reg_weights -> d final features (mirrors gmw_edge_weight_kernel) + running max of |G|
-__global__ void __launch_bounds__(256) edge_weight_bwd_tc_kernel(BwdTcArgs a, const float* __restrict__ grad_w) {
+// BW0: d reg_weights (+ optionally the gradient w.r.t. the NORMALISED features coming from the correspondence branch,
+// gn4 / gn6 [N][128][E]) -> d final features (mirrors gmw_edge_weight_kernel) + running max of |G|
+__global__ void __launch_bounds__(256) edge_weight_bwd_tc_kernel(BwdTcArgs a, const float* __restrict__ grad_w,
+                                                                 const float* __restrict__ gn4, const float* __restrict__ gn6) {
     const WsLayout& L = a.L;
     const int E = L.E, EP = L.EP, last = L.depth - 1;
     const int nb = (E + 255) / 256;
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(256) edge_weight_bwd_tc_kernel(BwdTcArgs a, co
         const float r4 = sqrtf(n4), r6 = sqrtf(n6);
         n4 = fmaxf(r4, 1e-12f);
         n6 = fmaxf(r6, 1e-12f);
-        float a2 = 0.f, c2 = 0.f, ac = 0.f;
+        float a2 = 0.f, c2 = 0.f, ac = 0.f, ag = 0.f, cg = 0.f;
+        const float* N4 = gn4 != nullptr ? gn4 + obj * (int64_t)CH * E + e : nullptr;
+        const float* N6 = gn6 != nullptr ? gn6 + obj * (int64_t)CH * E + e : nullptr;
         for (int c = 0; c < CH; ++c) {
             const float2 s4 = stat_s[0][c], s6 = stat_s[1][c];
             const float x4 = fmaxf((Y4[(int64_t)c * EP] - s4.x) * s4.y, 0.f) + X4[(int64_t)c * EP];
@@ -129,12 +133,14 @@ __global__ void __launch_bounds__(256) edge_weight_bwd_tc_kernel(BwdTcArgs a, co
             a2 = fmaf(av, av, a2);
             c2 = fmaf(cv, cv, c2);
             ac = fmaf(av, cv, ac);
+            if (N4 != nullptr) ag = fmaf(av, N4[(int64_t)c * E], ag);
+            if (N6 != nullptr) cg = fmaf(cv, N6[(int64_t)c * E], cg);
         }
         const float s = __fadd_rn(__fadd_rn(c2, -2.f * ac), a2);
         const float w = __fdiv_rn(1.f, sqrtf(fmaxf(s, 1e-30f)));
-        const float gw = __ldg(grad_w + obj * (int64_t)E + e);
+        const float gw = grad_w != nullptr ? __ldg(grad_w + obj * (int64_t)E + e) : 0.f;
         const float q = (s > 1e-30f) ? -0.5f * gw * w * w * w : 0.f;      // dL/ds, w = s^(-1/2)
-        const float ada = q * (2.f * a2 - 2.f * ac), cdc = q * (2.f * c2 - 2.f * ac);
+        const float ada = q * (2.f * a2 - 2.f * ac) + ag, cdc = q * (2.f * c2 - 2.f * ac) + cg;
         float* G4 = a.G + (obj * (int64_t)CH) * EP + e;
         float* G6 = a.G + ((L.N + obj) * (int64_t)CH) * EP + e;
         const bool live4 = r4 > 1e-12f, live6 = r6 > 1e-12f;
@@ -143,7 +149,8 @@ __global__ void __launch_bounds__(256) edge_weight_bwd_tc_kernel(BwdTcArgs a, co
             const float x4 = fmaxf((Y4[(int64_t)c * EP] - s4.x) * s4.y, 0.f) + X4[(int64_t)c * EP];
             const float x6 = fmaxf((Y6[(int64_t)c * EP] - s6.x) * s6.y, 0.f) + X6[(int64_t)c * EP];
             const float av = __fdiv_rn(x4, n4), cv = __fdiv_rn(x6, n6);
-            const float da = q * (2.f * av - 2.f * cv), dc = q * (2.f * cv - 2.f * av);
+            const float da = q * (2.f * av - 2.f * cv) + (N4 != nullptr ? N4[(int64_t)c * E] : 0.f);
+            const float dc = q * (2.f * cv - 2.f * av) + (N6 != nullptr ? N6[(int64_t)c * E] : 0.f);
             const float g4 = live4 ? (da - av * ada) / n4 : da / n4;
             const float g6 = live6 ? (dc - cv * cdc) / n6 : dc / n6;
             G4[(int64_t)c * EP] = g4;
@@ -600,7 +607,8 @@ size_t gmw_bwd_scratch_floats(int64_t N, int n, int depth) {
 }
 
 int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
-                           int64_t N, int n, int depth, const float* grad_reg_w, float* grad4, float* grad6,
+                           int64_t N, int n, int depth, const float* grad_reg_w, const float* grad_nfeat4,
+                           const float* grad_nfeat6, float* grad4, float* grad6,
                            float* ws, float* scratch, cudaStream_t st) {
     BwdTcArgs a;
     a.kpts2d = kpts2d; a.kpts3d = kpts3d;
@@ -627,7 +635,7 @@ int launch_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float
     const int ng = 2 * (3 * depth + 1);
     bwd_tc_init_kernel<<<(ng + 127) / 128, 128, 0, st>>>(a.gmax, ng);
     const unsigned g0 = (unsigned)(((a.L.E + 255) / 256) * N);
-    edge_weight_bwd_tc_kernel<<<g0, 256, 0, st>>>(a, grad_reg_w);
+    edge_weight_bwd_tc_kernel<<<g0, 256, 0, st>>>(a, grad_reg_w, grad_nfeat4, grad_nfeat6);
     const dim3 tgrid((unsigned)(a.L.T * N), 2);
     const dim3 grid((unsigned)ctas, 2);
     const dim3 rgrid((CH * CH + 255) / 256, 2, 2);

@@ -249,7 +249,7 @@ namespace {
 
 __global__ void __launch_bounds__(FTHREADS, 1)
 mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __restrict__ bias2, const uint32_t* __restrict__ wimg,
-                 float2* xg) {
+                 float2* xg, float* __restrict__ reg_w, float4* park) {
     const WsLayout& L = a.L;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
@@ -297,8 +297,15 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    const int64_t nitems = L.N * 2;
-    const int64_t item0 = group, item_step = gridDim.x / FCS;
+    // Work list of a group.  PAIRED (reg_w != nullptr): objects group, group + G, ... with both nets of an object back to
+    // back (net 0 then net 1), so that the second net's final pass finds the first net's features parked by the very
+    // same threads and emits the edge weights itself (see the epilogue).  Otherwise (features requested, or fewer
+    // objects than groups): items 2 obj + net dealt round-robin, final features to global memory.
+    const int64_t ngroups = gridDim.x / FCS;
+    const bool paired = reg_w != nullptr;
+    const int64_t nmine = (L.N > (int64_t)group) ? (L.N - 1 - group) / ngroups + 1 : 0;      // objects of this group when paired
+    const int64_t nitems = paired ? 2 * nmine : L.N * 2;
+    const int64_t item0 = paired ? 0 : group, item_step = paired ? 1 : ngroups;
 
     if (warp >= FCONV_WARPS) {
         // =====================================================================================================
@@ -404,7 +411,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         const float inv_em1 = 1.0f / (float)(E - 1);
 
         for (int64_t item = item0; item < nitems; item += item_step) {
-            const int64_t obj = item >> 1;
+            const int64_t obj = paired ? (int64_t)group + (item >> 1) * ngroups : (item >> 1);
             const int net = (int)(item & 1);
             const int cin = net == 0 ? 4 : 6;
             const float* __restrict__ prm = a.params[net];
@@ -683,34 +690,108 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 b_in = b_out;
             }
 
-            // ---- final features x = relu(cn(Y2)) + X -> global, channel-major [obj][128][EP]
-            {
-                const float a_in = un_in * st.y, c_in = (b_in - st.x) * st.y;
+            // ---- final features x = relu(cn(Y2)) + X
+            const float a_fin = un_in * st.y, c_fin = (b_in - st.x) * st.y;
+            auto final_unit = [&](int col0, float (&v)[16]) {
+                const float4* Xp = Xs + (col0 >> 2) * CH + ch;
+                float4 x4[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                tmem_ld16(t_lane + col0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_fin, c_fin), 0.f);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
+                }
+                if (col0 + 16 > valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (col0 + i >= valid) v[i] = 0.f;
+                }
+            };
+            if (!paired) {
+                // -> global, channel-major [obj][128][EP] (consumed by gmw_edge_weight_kernel / the correspondence branch)
                 float* G = act_ptr(a.ws, L, net, 0, SLOT_X) + obj * (int64_t)CH * EP + (int64_t)ch * EP + e_base;
                 for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
                     float v[16];
-                    const float4* Xp = Xs + (col0 >> 2) * CH + ch;
-                    float4 x4[4];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
-                    tmem_ld16(t_lane + col0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_in, c_in), 0.f);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
-                    }
-                    if (col0 + 16 > valid) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (col0 + i >= valid) v[i] = 0.f;
-                    }
+                    final_unit(col0, v);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
                         __stcs(reinterpret_cast<float4*>(G + col0 + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));   // streamed: keep the weight image in L2
                 }
-                tc_fence_before();                            // the next item's MMAs overwrite these columns
+            } else if (net == 0) {
+                // park the 4-d net's features in this CTA's slice of an L2-resident scratch ([ES/4][128] float4 like Xs): the
+                // thread that writes a word is the one that reads it back after the 6-d net, so no fence or barrier is needed
+                float4* Pk = park + ((size_t)blockIdx.x * (FES_MAX / 4)) * CH + ch;
+                for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
+                    float v[16];
+                    final_unit(col0, v);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) Pk[((col0 >> 2) + q4) * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                }
+            } else {
+                // edge weights straight from the two nets' final features (GMW/model/model.py:176-181, diagonal of pairwiseL2Dist):
+                // per edge the three channel sums |a|^2, |c|^2, a.c — 32 channels by a halving shuffle tree, the 4 lane quarters
+                // through shared memory (the operand buffers are idle here) — then
+                //   w = 1 / sqrt(max((|c^|^2 - 2 a^.c^) + |a^|^2, 1e-30)),  a^ = a / max(|a|, 1e-12)
+                const float4* Pk = park + ((size_t)blockIdx.x * (FES_MAX / 4)) * CH + ch;
+                float* red = reinterpret_cast<float*>(Bbuf) + wg * (2 * 4 * 48);      // [2 buffers][4 quarters][16 edges][3]
+                float* W = reg_w + obj * (int64_t)E + e_base;
+                int itn = 0;
+                for (int col0 = 16 * wg; col0 < ES; col0 += FSUB, ++itn) {
+                    float cv[16], aa[16], cc[16], ac[16];
+                    final_unit(col0, cv);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float4 p = Pk[((col0 >> 2) + q4) * CH];
+                        const float av[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float c = cv[4 * q4 + i];
+                            aa[4 * q4 + i] = av[i] * av[i];
+                            cc[4 * q4 + i] = c * c;
+                            ac[4 * q4 + i] = av[i] * c;
+                        }
+                    }
+                    // halving tree over the 32 lanes: afterwards lane l holds the sums of edge l >> 1
+#pragma unroll
+                    for (int h = 8; h >= 1; h >>= 1) {
+                        const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+                        for (int k = 0; k < h; ++k) {
+                            const float sa = up ? aa[k] : aa[k + h], sc = up ? cc[k] : cc[k + h], sx = up ? ac[k] : ac[k + h];
+                            const float ka = up ? aa[k + h] : aa[k], kc = up ? cc[k + h] : cc[k], kx = up ? ac[k + h] : ac[k];
+                            aa[k] = ka + __shfl_xor_sync(0xffffffffu, sa, 2 * h);
+                            cc[k] = kc + __shfl_xor_sync(0xffffffffu, sc, 2 * h);
+                            ac[k] = kx + __shfl_xor_sync(0xffffffffu, sx, 2 * h);
+                        }
+                    }
+                    aa[0] += __shfl_xor_sync(0xffffffffu, aa[0], 1);
+                    cc[0] += __shfl_xor_sync(0xffffffffu, cc[0], 1);
+                    ac[0] += __shfl_xor_sync(0xffffffffu, ac[0], 1);
+                    float* rb = red + (itn & 1) * (4 * 48);
+                    if ((lane & 1) == 0) {
+                        float* o = rb + quarter * 48 + (lane >> 1) * 3;
+                        o[0] = aa[0]; o[1] = cc[0]; o[2] = ac[0];
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");       // the 4 warps (lane quarters) of this unit
+                    if (quarter == 0 && lane < 16) {
+                        const int e = col0 + lane;
+                        if (e < valid) {
+                            const float* o = rb + lane * 3;
+                            const float saa = (o[0] + o[48]) + (o[96] + o[144]);
+                            const float scc = (o[1] + o[49]) + (o[97] + o[145]);
+                            const float sac = (o[2] + o[50]) + (o[98] + o[146]);
+                            const float n4 = fmaxf(sqrtf(saa), 1e-12f), n6 = fmaxf(sqrtf(scc), 1e-12f);
+                            const float a2 = __fdiv_rn(saa, n4 * n4), c2 = __fdiv_rn(scc, n6 * n6), acn = __fdiv_rn(sac, n4 * n6);
+                            const float s2 = __fadd_rn(__fadd_rn(c2, -2.f * acn), a2);
+                            W[e] = __fdiv_rn(1.f, sqrtf(fmaxf(s2, 1e-30f)));
+                        }
+                    }
+                }
             }
+            tc_fence_before();                                // the next item's MMAs overwrite these columns
         }
     }
     tc_fence_before();
@@ -748,9 +829,13 @@ size_t gmw_fused_image_bytes(int depth) {
     return fused_scales_bytes(depth) + fused_bias_bytes(depth) + fused_image_only_bytes(depth) + kExchangeBytes;
 }
 
-// Runs both nets of all objects; the final features land in SLOT_X of the (inference-layout) workspace.
+// Runs both nets of all objects.  reg_w != nullptr and at least as many objects as groups: PAIRED schedule, the kernel emits
+// the edge weights itself (*emitted = true; nothing but reg_w is written to HBM; the first net's features are parked in the
+// otherwise unused SLOT_Y1 area of the inference workspace, one object's worth per group, which stays in L2).  Otherwise the
+// final features land in SLOT_X of the workspace (*emitted = false) for gmw_edge_weight_kernel / the correspondence branch.
 // `tail` points to gmw_fused_image_bytes(depth) bytes (256-byte aligned).
-int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st) {
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, float* reg_w, bool* emitted,
+                         cudaStream_t st) {
     const int depth = a.L.depth;
     unsigned char* base = reinterpret_cast<unsigned char*>(tail);
     float2* scales2 = reinterpret_cast<float2*>(base);
@@ -772,18 +857,22 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
     if (max_groups < 1) return DCD_E_UNSUPPORTED;
     fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, a.fold, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
-    const int64_t nitems = a.L.N * 2;
+    const bool paired = reg_w != nullptr && a.L.N >= max_groups;
+    const int64_t nitems = paired ? a.L.N : a.L.N * 2;
     const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);
     MlpArgs args = a;
     const float2* scales_arg = scales2;
     const float* bias_arg = bias2;
     const uint32_t* wimg_arg = wimg;
-    void* kargs[] = {&args, &scales_arg, &bias_arg, &wimg_arg, &xg};
+    float* regw_arg = paired ? reg_w : nullptr;
+    float4* park_arg = reinterpret_cast<float4*>(act_ptr(a.ws, a.L, 0, 0, SLOT_Y1));
+    void* kargs[] = {&args, &scales_arg, &bias_arg, &wimg_arg, &xg, &regw_arg, &park_arg};
     if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mlp_fused_kernel), dim3(FCS * ngroups), dim3(FTHREADS), kargs, kFusedSmem,
                                     st) != cudaSuccess) {
         cudaGetLastError();
         return DCD_E_LAUNCH;
     }
+    *emitted = paired;
     return DCD_OK;
 }
 

@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
 // bytes appended to the MLP workspace for the per-matrix FP16 scales (scale, 1/scale)
 bool gmw_fused_supported(int n);
 size_t gmw_fused_image_bytes(int depth);
-int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, cudaStream_t st);
+int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, float* reg_w, bool* emitted,
+                         cudaStream_t st);
 
 static size_t tc_scales_bytes(int depth) { return (((size_t)2 * depth * 3 * sizeof(float2)) + 255) / 256 * 256; }
 static size_t tc_fold_bytes(int depth) {                  // folded layers + their running maxima (one int per matrix)
@@ -507,9 +508,12 @@ int launch_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float
     if (!save && gmw_fused_supported(n) && !force_layerwise()) {
         // inference: whole network on chip, one kernel (gmw_mlp_fused.cu)
         a.fold = launch_fold_prep(params4, params6, depth, scales, false, st);
-        const int rc = launch_gmw_fused_fwd(a, params4, params6, reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth), st);
+        // the edge weights come out of the fused kernel itself unless the final features are wanted too
+        bool emitted = false;
+        const int rc = launch_gmw_fused_fwd(a, params4, params6, reinterpret_cast<unsigned char*>(scales) + tc_scales_bytes(depth),
+                                            (feat4 == nullptr && feat6 == nullptr) ? reg_w : nullptr, &emitted, st);
         if (rc != DCD_OK) return rc;
-        gmw_edge_weight_kernel<true><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
+        if (!emitted) gmw_edge_weight_kernel<true><<<g2, 256, 0, st>>>(a, reg_w, feat4, feat6);
         DCD_CHECK_LAUNCH();
         return DCD_OK;
     }

@@ -30,6 +30,7 @@ DGDE_CLAMP = (2.0, 80.0)     # anno_encoder.py:375
 GMW_CLAMP = (0.1, 80.0)      # GMW/main.py:410
 FLAG_NORMALISE_2D = 1
 FLAG_SUB_B3 = 2
+FLAG_FAST_QUOTIENT = 4
 MAX_KPTS = 256
 
 
@@ -188,11 +189,12 @@ def decode_pairs_kpts_depth(kps, kps_3d, rot_y, K, training=False, kpts_2d_mask=
     return (depth, mask, idx) if return_idx else (depth, mask)
 
 
-def edge_depth_mean(kps, kps_3d, rot_y, K, training=False, num_k: int = K_SEL) -> torch.Tensor:
+def edge_depth_mean(kps, kps_3d, rot_y, K, training=False, num_k: int = K_SEL, fast: bool = False) -> torch.Tensor:
     """Fused `decode_pairs_kpts_depth(...)[0].mean(1)` (detector_infer.py:222-225, detector_loss.py:388):
-    per-object depth [N] without materialising the per-edge depths."""
+    per-object depth [N] without materialising the per-edge depths.  `fast=True` (inference, large batches) trades the
+    IEEE division for the hardware reciprocal: per-object depth within 1e-6 (relative) of the default, see DCD_FAST_QUOTIENT."""
     kps, kps_3d, rot, K = _prep_dgde(kps, kps_3d, rot_y, K)
-    flags = FLAG_NORMALISE_2D | FLAG_SUB_B3
+    flags = FLAG_NORMALISE_2D | FLAG_SUB_B3 | (FLAG_FAST_QUOTIENT if fast and not training else 0)
     lo, hi = DGDE_CLAMP
     if not training:
         return _EdgeSolve.apply(kps, kps_3d, rot, K, lo, hi, flags, False, True)[1]
@@ -422,10 +424,71 @@ class _GmwWeights(torch.autograd.Function):
             g = f32c(g_reg_w)
             scratch = _alloc_bytes(L.dcd_gmw_bwd_scratch_bytes(N, n, ctx.depth), g.device)
             check(L.dcd_gmw_weights_bwd(ptr(kpts_2d), ptr(kpts_3d), ptr(params4), ptr(params6), N, n, ctx.depth,
-                                        ptr(g), ptr(g4), ptr(g6), ptr(ctx.ws), ctx.ws.numel() * 4,
+                                        ptr(g), 0, 0, ptr(g4), ptr(g6), ptr(ctx.ws), ctx.ws.numel() * 4,
                                         ptr(scratch), scratch.numel() * 4, stream_ptr()), "dcd_gmw_weights_bwd")
         ctx.ws = None
         return None, None, g4, g6, None, None
+
+
+SINKHORN_CG_ITERATIONS, SINKHORN_CG_TOLERANCE = 32, 1e-7
+
+
+class _GmwWeightsTransport(torch.autograd.Function):
+    """GMW.forward with both outputs like the reference (GMW/model/model.py:195-207): reg_weights [b,E] and the Sinkhorn
+    transport plan edge_P [b,E,E], both differentiable w.r.t. the parameter blobs.  Backward = implicit gradient of the
+    Sinkhorn fixed point (optimal_transport.py:75-128 as one conjugate-gradient solve) -> feature gradients -> MLP backward."""
+
+    @staticmethod
+    def forward(ctx, kpts_2d, kpts_3d, params4, params6, depth, need_grad, lam, tol, iters):
+        N, n = kpts_2d.shape[0], kpts_2d.shape[1]
+        E = _num_edges(n)
+        dev = kpts_2d.device
+        L = _lib.lib()
+        reg_w = torch.empty((N, E), dtype=torch.float32, device=dev)
+        P = torch.empty((N, E, E), dtype=torch.float32, device=dev)
+        u = torch.empty((N, E), dtype=torch.float32, device=dev)
+        v = torch.empty((N, E), dtype=torch.float32, device=dev)
+        f4 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
+        f6 = torch.empty((N, 128, E), dtype=torch.float32, device=dev)
+        save = 1 if need_grad else 0
+        ws = None
+        if N:
+            ws = _alloc_bytes(L.dcd_gmw_workspace_bytes(N, n, depth, save), dev)
+            check(L.dcd_gmw_weights_fwd(ptr(kpts_2d), ptr(kpts_3d), ptr(params4), ptr(params6), N, n, depth, save,
+                                        ptr(reg_w), ptr(f4), ptr(f6), ptr(ws), ws.numel() * 4, stream_ptr()), "dcd_gmw_weights_fwd")
+            tws = _alloc_bytes(L.dcd_gmw_transport_workspace_bytes(N, n), dev)
+            check(L.dcd_gmw_transport_fwd(ptr(f4), ptr(f6), N, n, lam, tol, iters, ptr(P), ptr(u), ptr(v), 0,
+                                          ptr(tws), tws.numel() * 4, stream_ptr()), "dcd_gmw_transport_fwd")
+        if need_grad:
+            ctx.save_for_backward(kpts_2d, kpts_3d, params4, params6, f4, f6, P, u, v)
+            ctx.ws = ws
+            ctx.cfg = (depth, lam)
+        return reg_w, P
+
+    @staticmethod
+    def backward(ctx, g_reg_w, g_P):
+        kpts_2d, kpts_3d, params4, params6, f4, f6, P, u, v = ctx.saved_tensors
+        depth, lam = ctx.cfg
+        N, n = kpts_2d.shape[0], kpts_2d.shape[1]
+        L = _lib.lib()
+        g4 = torch.zeros_like(params4)
+        g6 = torch.zeros_like(params6)
+        if N and (g_reg_w is not None or g_P is not None):
+            gn4 = gn6 = None
+            if g_P is not None:
+                gP = f32c(g_P)
+                gn4, gn6 = torch.empty_like(f4), torch.empty_like(f6)
+                tws = _alloc_bytes(L.dcd_gmw_transport_bwd_workspace_bytes(N, n), gP.device)
+                check(L.dcd_gmw_transport_bwd(ptr(f4), ptr(f6), ptr(P), ptr(u), ptr(v), ptr(gP), N, n, lam,
+                                              SINKHORN_CG_ITERATIONS, SINKHORN_CG_TOLERANCE, ptr(gn4), ptr(gn6), 0,
+                                              ptr(tws), tws.numel() * 4, stream_ptr()), "dcd_gmw_transport_bwd")
+            g = f32c(g_reg_w) if g_reg_w is not None else None
+            scratch = _alloc_bytes(L.dcd_gmw_bwd_scratch_bytes(N, n, depth), kpts_2d.device)
+            check(L.dcd_gmw_weights_bwd(ptr(kpts_2d), ptr(kpts_3d), ptr(params4), ptr(params6), N, n, depth,
+                                        ptr(g), ptr(gn4), ptr(gn6), ptr(g4), ptr(g6), ptr(ctx.ws), ctx.ws.numel() * 4,
+                                        ptr(scratch), scratch.numel() * 4, stream_ptr()), "dcd_gmw_weights_bwd")
+        ctx.ws = None
+        return None, None, g4, g6, None, None, None, None, None
 
 
 class _GmwAggregate(torch.autograd.Function):
@@ -458,9 +521,10 @@ class GMW(nn.Module):
 
     forward(kpts_2d, kpts_3d, pred_rot, args) -> (reg_weights [b,E], edge_P); `pred_rot` and `args`
     are ignored as in the reference.  edge_P (the Sinkhorn correspondence matrix
-    of the classification branch) is returned as None by forward(); its forward
-    (no gradient) is available through `edge_transport`, and forward() returns it too when the module
-    attribute `with_edge_P` is set and gradients are disabled (validation loop of GMW/main.py:524-527).
+    of the classification branch) is None unless the module attribute `with_edge_P`
+    is set (dcd_b200.patch.install sets it: both loops of GMW/main.py consume edge_P, :456 and :526); then it
+    is the [b,E,E] transport plan, differentiable like the reference's (implicit Sinkhorn gradient,
+    optimal_transport.py:75-128).  `edge_transport` gives the plan's (sum, trace) without materialising it.
     Parameters live in two flat blobs; `load_state_dict`/`state_dict` of the *reference* format
     are available through `load_reference_state_dict` / `reference_state_dict`.
     """
@@ -533,11 +597,9 @@ class GMW(nn.Module):
         if k2.dim() != 3 or k2.shape[-1] != 2 or tuple(k3.shape) != (k2.shape[0], k2.shape[1], 3):
             raise ValueError("kpts_2d must be [b,n,2] and kpts_3d [b,n,3]")
         need_grad = torch.is_grad_enabled() and (params4.requires_grad or params6.requires_grad)
-        if self.with_edge_P and not need_grad:
-            reg_w, P, _ = self.edge_transport(k2, k3, params=(params4, params6))
-            return reg_w, P
         if self.with_edge_P:
-            raise NotImplementedError("dcd_b200.GMW: edge_P under autograd (the Sinkhorn backward) is not available in this build")
+            return _GmwWeightsTransport.apply(k2, k3, params4, params6, self.depth, need_grad, self.SINKHORN_LAMBDA,
+                                              self.SINKHORN_TOLERANCE, self.SINKHORN_ITERATIONS)
         reg_w = _GmwWeights.apply(k2, k3, params4, params6, self.depth, need_grad)
         if _CHECK_FINITE and not bool(torch.isfinite(reg_w).all()):
             # the tensor-core path carries activations as FP16 hi+lo pairs: |activation| must stay below 65504

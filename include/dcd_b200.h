@@ -26,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define DCD_ABI_VERSION 1
+#define DCD_ABI_VERSION 2
 
 /* status codes */
 #define DCD_OK              0
@@ -39,6 +39,9 @@ extern "C" {
 /* flags of the edge solve */
 #define DCD_NORMALISE_2D    1   /* v = (kps_v - K[1][2]) / K[1][1]   (DGDE form, anno_encoder.py:331-334) */
 #define DCD_SUB_B3          2   /* subtract K[2][3] after the clamp   (DGDE form, anno_encoder.py:385)     */
+#define DCD_FAST_QUOTIENT   4   /* fused mean only (depth_edges == NULL, large N): |H| * rcp(|V|) with the 1-ulp hardware
+                                   reciprocal instead of the IEEE division; per-object mean within 1e-6 (relative) of the
+                                   exact one, per-edge values not bit-faithful.  Opt-in; ignored otherwise. */
 
 #define DCD_MAX_KPTS      256   /* pair ids are packed in 16 bits */
 #define DCD_NET_CH        128   /* channels of the edge MLP (yi2018cvpr/config.py:72) */
@@ -159,20 +162,36 @@ int dcd_gmw_weights_fwd(const float* kpts2d, const float* kpts3d, const float* p
  * P = Sinkhorn(M; r = c = 1/E, lambda, tolerance, max_iterations) (GMW/lib/optimal_transport.py:52-72, model.py:186-191).
  * Outputs (each may be NULL): P [N,E,E], u / v [N,E] (P = diag(u) K diag(v), K = exp(-lambda min(M,5))),
  * sums [N,2] = (sum P, trace P) — correspondenceLoss(P, eye) = mean over objects of sum - 2 trace (lib/losses.py:22-26,
- * 115-119; GMW/main.py:456-457,526-527).  The workspace holds K (4 E^2 bytes per object); N <= 65535.  No backward. */
+ * 115-119; GMW/main.py:456-457,526-527).  The workspace holds K (4 E^2 bytes per object); N <= 65535. */
 size_t dcd_gmw_transport_workspace_bytes(int64_t N, int n);
 int dcd_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, int n, float lambda, float tolerance,
                           int max_iterations, float* P, float* u, float* v, float* sums, void* workspace,
                           size_t workspace_bytes, void* stream);
 
-/* Backward of dcd_gmw_weights_fwd w.r.t. the parameters (autograd of GMW/main.py:465 on the reg path).
- * workspace: the one filled by the forward call with save=1 (same N, n, depth).  grad_reg_weights [N,E].
+/* Backward of dcd_gmw_transport_fwd (RegularisedTransportFn.backward, GMW/lib/optimal_transport.py:75-128,184-222, then
+ * the autograd of pairwiseL2Dist, GMW/model/model.py:17-36): from grad_P [N,E,E] = dL/dP to the gradient w.r.t. the
+ * L2-NORMALISED features, grad_nfeat4 / grad_nfeat6 [N,128,E] (feed them to dcd_gmw_weights_bwd).  P, u, v: outputs of the
+ * forward call; feat4 / feat6: its inputs.  The reference's E x E Cholesky + inverse + three E^3 products are replaced by
+ * ONE matrix-free conjugate-gradient solve of the same SPD system (two passes over P per iteration; relative residual
+ * cg_tolerance, at most max_cg_iterations, typically 6-20) — see csrc/gmw_transport_bwd.cu.  cg_info (may be NULL) [N,8]:
+ * (final |r|^2, initial |r|^2, converged flag, iterations, -, -, -, -) per object. */
+size_t dcd_gmw_transport_bwd_workspace_bytes(int64_t N, int n);
+int dcd_gmw_transport_bwd(const float* feat4, const float* feat6, const float* P, const float* u, const float* v,
+                          const float* grad_P, int64_t N, int n, float lambda, int max_cg_iterations, float cg_tolerance,
+                          float* grad_nfeat4, float* grad_nfeat6, float* cg_info, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Backward of dcd_gmw_weights_fwd w.r.t. the parameters (autograd of GMW/main.py:465).
+ * workspace: the one filled by the forward call with save=1 (same N, n, depth).  grad_reg_weights [N,E] (reg path) and/or
+ * grad_nfeat4 / grad_nfeat6 [N,128,E] (gradient w.r.t. the normalised final features, from dcd_gmw_transport_bwd: cls path);
+ * each may be NULL, not all three.
  * grad_params4 / grad_params6: same layout as the parameter blobs, OVERWRITTEN with the sum over the N
  * objects.  Deterministic (per-CTA partial sums reduced in a fixed order).
  */
 size_t dcd_gmw_bwd_scratch_bytes(int64_t N, int n, int depth);
 int dcd_gmw_weights_bwd(const float* kpts2d, const float* kpts3d, const float* params4, const float* params6,
                         int64_t N, int n, int depth, const float* grad_reg_weights,
+                        const float* grad_nfeat4, const float* grad_nfeat6,
                         float* grad_params4, float* grad_params6,
                         void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                         void* stream);

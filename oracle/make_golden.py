@@ -395,5 +395,119 @@ def main():
     transport_fixture("transport_n73_N2", N=2, seed=synth.BASE_SEED + 25, wseed=7)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "round2"):
     main()
+
+
+def transport_bwd_fixture(name, E, N, seed, sharp=0.0, store_full=True):
+    """Row N1 backward at the feature level: the unmodified pairwiseL2Dist (GMW/model/model.py:17-36) + RegularisedTransport
+    (GMW/lib/optimal_transport.py, forward :52-72 and the implicit backward :75-128,184-222) on given edge features
+    [N,E,128]; gradients of  sum(V * P)  w.r.t. the L2-normalised features, V = the correspondence-loss weights
+    (1 - 2 eye) / N of GMW/main.py:456-457 for object 0.. and a random V for the last object.  FP32 (the reference as it
+    runs) and FP64 (the same code in double: the conditioning anchor).  sharp > 0 makes f6 ~ f4 + sharp * noise: a
+    trained-like, nearly diagonal plan."""
+    rl.load_gmw()
+    from model.model import pairwiseL2Dist
+    from lib.optimal_transport import RegularisedTransport
+    g = torch.Generator().manual_seed(seed)
+    f4 = torch.randn(N, E, 128, generator=g) * (0.5 + torch.rand(N, E, 1, generator=g))
+    f6 = (f4 + sharp * torch.randn(N, E, 128, generator=g)) if sharp > 0 else torch.randn(N, E, 128, generator=g) * 1.3
+    V = ((1.0 - 2.0 * torch.eye(E)) / N).expand(N, E, E).clone()
+    V[-1] = torch.randn(E, E, generator=g) / N
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        a = torch.nn.functional.normalize(f4.to(dt), p=2, dim=-1).requires_grad_(True)
+        c = torch.nn.functional.normalize(f6.to(dt), p=2, dim=-1).requires_grad_(True)
+        M = pairwiseL2Dist(a, c)
+        r = M.new_ones((N, E)) / E
+        cc = M.new_ones((N, E)) / E
+        P = RegularisedTransport(10.0, 1e-9)(M, r, cc)
+        (P * V.to(dt)).sum().backward()
+        res[dt] = (P.detach(), a.grad.detach(), c.grad.detach())
+    P32, ga32, gc32 = res[torch.float32]
+    P64, ga64, gc64 = res[torch.float64]
+    out = dict(E=np.array(E), N=np.array(N), seed=np.array(seed), sharp=np.array(sharp),
+               P_sum=npy(P32.sum((-2, -1))), P_trace=npy(P32.diagonal(dim1=-2, dim2=-1).sum(-1)),
+               P_trace_f64=npy(P64.diagonal(dim1=-2, dim2=-1).sum(-1)))
+    if store_full:
+        out.update(feat4=npy(f4), feat6=npy(f6), V=npy(V), grad_a=npy(ga32), grad_c=npy(gc32), grad_a_f64=npy(ga64), grad_c_f64=npy(gc64))
+    else:       # inputs are regenerated from the seed by the test (same torch.Generator stream); gradients sampled
+        out.update(grad_a=npy(ga32[:, ::16, :]), grad_c=npy(gc32[:, ::16, :]), grad_a_f64=npy(ga64[:, ::16, :]),
+                   grad_c_f64=npy(gc64[:, ::16, :]), V_last_sample=npy(V[-1, ::97, ::97]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    e32 = max(float((ga32.double() - ga64).abs().max() / ga64.abs().max()), float((gc32.double() - gc64).abs().max() / gc64.abs().max()))
+    print(name, "trace P", P64.diagonal(dim1=-2, dim2=-1).sum(-1).tolist(), "reference FP32 vs FP64 gradient (rel max)", e32)
+
+
+def transport_inputs(E, N, seed, sharp):
+    """The inputs of transport_bwd_fixture(store_full=False), regenerated from the seed."""
+    g = torch.Generator().manual_seed(seed)
+    f4 = torch.randn(N, E, 128, generator=g) * (0.5 + torch.rand(N, E, 1, generator=g))
+    f6 = (f4 + sharp * torch.randn(N, E, 128, generator=g)) if sharp > 0 else torch.randn(N, E, 128, generator=g) * 1.3
+    V = ((1.0 - 2.0 * torch.eye(E)) / N).expand(N, E, E).clone()
+    V[-1] = torch.randn(E, E, generator=g) / N
+    return f4, f6, V
+
+
+def gmw_train_fixture(name, N, seed, wseed, cls_weight, reg_weight):
+    """One training step's loss and gradients through the UNMODIFIED reference (GMW/main.py:453-465): compute_z, GMW.forward
+    (both outputs), correspondenceLoss(edge_P, eye), compute_reg_loss, loss = cls_weight * cls + reg_weight * reg, backward
+    (incl. RegularisedTransportFn.backward) — in FP32 as the reference runs and in FP64 (same modules in double) as the
+    conditioning anchor.  Stores per-tensor norms, max-norms and a 1/61 sample of every gradient in both precisions."""
+    main, _ = rl.load_gmw()
+    from lib.losses import correspondenceLoss
+    ob = synth.make_objects(N=N, n=73, seed=seed)
+    sd = O.random_state_dict(wseed)
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        model = rl.new_gmw_model(0)
+        model.load_state_dict(sd, strict=True)
+        model = model.to(dt).train()
+        k2, k3, rot, gt = ob.kps_norm.to(dt), ob.kps_3d.to(dt), ob.rot_y.to(dt), ob.gt_depth.to(dt)
+        with torch.no_grad():
+            Z, _ = main.compute_z(k2, k3, rot)
+        _, idx_c = O.compute_z(ob.kps_norm, ob.kps_3d, ob.rot_y, canonical=True)       # FP32 keys: same selection in both runs
+        w, P = model(k2, k3, rot, None)
+        eye = torch.eye(P.shape[1], dtype=dt).expand_as(P)
+        cls = correspondenceLoss(P, eye)
+        reg, zsel = main.compute_reg_loss(Z, w, gt, idx_c)
+        loss = cls_weight * cls + reg_weight * reg
+        model.zero_grad()
+        loss.backward()
+        res[dt] = (float(cls), float(reg), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    names = list(res[torch.float32][2].keys())
+    g32, g64 = res[torch.float32][2], res[torch.float64][2]
+    out = inputs_dict(ob)
+    out.update(weight_seed=np.array(wseed), cls_weight=np.array(cls_weight), reg_weight=np.array(reg_weight),
+               cls_loss=np.array(res[torch.float32][0]), reg_loss=np.array(res[torch.float32][1]),
+               cls_loss_f64=np.array(res[torch.float64][0]), reg_loss_f64=np.array(res[torch.float64][1]),
+               grad_names=np.array(names),
+               grad_sample=npy(torch.cat([g32[k].reshape(-1) for k in names])[::61]),
+               grad_sample_f64=npy(torch.cat([g64[k].reshape(-1) for k in names])[::61]),
+               grad_absmax_f64=np.array([float(g64[k].abs().max()) for k in names]),
+               grad_ref_err=np.array([float((g32[k].double() - g64[k]).abs().max()) for k in names]),
+               grad_conv_in4_w_f64=npy(g64["FeatureExtractor4d.conv_in.0.weight"]),
+               grad_last6_w_f64=npy(g64["FeatureExtractor6d.conv_11.conv2.0.weight"]),
+               grad_conv_in4_w=npy(g32["FeatureExtractor4d.conv_in.0.weight"]),
+               grad_last6_w=npy(g32["FeatureExtractor6d.conv_11.conv2.0.weight"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    worst = max(float((g32[k].double() - g64[k]).abs().max() / max(float(g64[k].abs().max()), 1e-30)) for k in names
+                if float(g64[k].abs().max()) > 1e-6)
+    print(name, "cls %.6f reg %.6f; reference FP32 vs FP64 weight gradients, worst tensor (rel max-norm) %.3g" % (
+        res[torch.float32][0], res[torch.float32][1], worst))
+
+
+def main_round2():
+    """Fixtures added in round 2 (the Sinkhorn backward and the full training loss)."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    transport_bwd_fixture("transport_bwd_E190_N3", E=190, N=3, seed=synth.BASE_SEED + 30)
+    transport_bwd_fixture("transport_bwd_E190_sharp", E=190, N=2, seed=synth.BASE_SEED + 31, sharp=0.05)
+    transport_bwd_fixture("transport_bwd_E2628_N2", E=2628, N=2, seed=synth.BASE_SEED + 32, store_full=False)
+    transport_bwd_fixture("transport_bwd_E2628_sharp", E=2628, N=1, seed=synth.BASE_SEED + 33, sharp=0.03, store_full=False)
+    gmw_train_fixture("gmw_train_n73_N2", N=2, seed=synth.BASE_SEED + 34, wseed=7, cls_weight=1.0, reg_weight=0.0)
+    gmw_train_fixture("gmw_train_n73_N2_reg", N=2, seed=synth.BASE_SEED + 35, wseed=7, cls_weight=0.1, reg_weight=1.0)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "round2":
+    main_round2()

@@ -42,7 +42,7 @@ def test_library_has_no_torch_dependency():
 
 
 def test_version_strerror_and_size_queries(lib):
-    assert lib.dcd_version() == 1
+    assert lib.dcd_version() == 2
     assert lib.dcd_strerror(0) == b"ok"
     assert b"workspace" in lib.dcd_strerror(-2)
     assert lib.dcd_gmw_param_count(4, 12) == 595072 and lib.dcd_gmw_param_count(6, 12) == 595328
