@@ -606,9 +606,18 @@ def kitti_val_stages(ctx, ob, d_k2, d_k3, d_rot, model):
             loss.backward()
             if world > 1:
                 ddist.allreduce_gradients(train_model)
-        return train_step, train_model, (t_k2, t_k3)
-    train8, train_model, (t_k2, t_k3) = make_train_step(8)
+        return train_step, train_model, (t_k2, t_k3, t_rot, t_gt)
+    train8, train_model, (t_k2, t_k3, t_rot8, t_gt8) = make_train_step(8)
     ms_train = time_kernel(train8, reps=5)
+    # the same step replayed from a CUDA graph (one launch instead of ~80)
+    graph_model = dcd_b200.GMW().to(dev).load_reference_state_dict(synth.random_state_dict(WEIGHT_SEED))
+    gstep = dcd_b200.GraphedGmwStep(graph_model, batch=8, n=N_KPTS)
+
+    def train8_graph():
+        gstep(t_k2, t_k3, t_rot8, t_gt8)
+        if world > 1:
+            ddist.allreduce_gradients(graph_model)
+    ms_train_graph = time_kernel(train8_graph, reps=10)
     train64, _, _ = make_train_step(64)
     ms_train64 = time_kernel(train64, reps=3, warm=2)
     # correspondence branch, forward: E x E distances + Sinkhorn for the same 8 objects, P not materialised
@@ -663,6 +672,9 @@ def kitti_val_stages(ctx, ob, d_k2, d_k3, d_rot, model):
         "gmw_train_step_b8": {"ms": ms_train, "objects_per_s": 8 * world / (ms_train * 1e-3),
                               "what": "configs[2]: compute_z + edge MLP fwd + softmax aggregate + L1 loss + full backward (all GEMMs on "
                                       "tcgen05) for 8 objects per GPU%s; optimizer step excluded" % (" + gradient all-reduce" if world > 1 else "")},
+        "gmw_train_step_b8_cuda_graph": {"ms": ms_train_graph, "objects_per_s": 8 * world / (ms_train_graph * 1e-3),
+                                         "what": "the same step captured once in a CUDA graph (dcd_b200.GraphedGmwStep) and replayed; inputs "
+                                                 "copied into the static buffers inside the timed region"},
         "gmw_train_step_b64": {"ms": ms_train64, "objects_per_s": 64 * world / (ms_train64 * 1e-3),
                                "mlp_tflops": 3 * F_MLP * 64 / (ms_train64 * 1e-3) / 1e12,
                                "what": "the same step at 64 objects per GPU (fwd + bwd = 3 x the folded forward GEMM FLOPs)"},

@@ -8,10 +8,14 @@ Host-side helpers: patch (attribute-patch the reference), dist (frame sharding +
 weights (state_dict <-> parameter blob), synth (seeded KITTI-shaped objects), build (nvcc).
 """
 from .ops import (GMW, K_SEL, compute_pairs_kpts_depth, compute_reg_loss, compute_z, decode_depth_from_keypoints_batch,
-                  decode_location_flatten, decode_pairs_kpts_depth, depth_ensemble, edge_depth_mean, gmw_weighted_depth,
-                  ray_rescale, select_point_of_interest)
+                  decode_location_flatten, decode_pairs_kpts_depth, depth_ensemble, edge_depth_mean, frame_depths_from_map,
+                  gmw_weighted_depth, ray_rescale, select_point_of_interest)
 
 __all__ = ["GMW", "K_SEL", "compute_pairs_kpts_depth", "compute_reg_loss", "compute_z", "decode_depth_from_keypoints_batch",
-           "decode_location_flatten", "decode_pairs_kpts_depth", "depth_ensemble", "edge_depth_mean", "gmw_weighted_depth",
+           "decode_location_flatten", "decode_pairs_kpts_depth", "depth_ensemble", "edge_depth_mean", "frame_depths_from_map",
+           "gmw_weighted_depth",
            "ray_rescale", "select_point_of_interest"]
-__version__ = "0.1.0"
+from .graphs import GraphedGmwStep  # noqa: E402
+
+__all__.append("GraphedGmwStep")
+__version__ = "0.2.0"

@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 import torch
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdcd_b200.so")
+# DCD_B200_LIB selects a debug variant of the library built by `python -m dcd_b200.build --trace` (profiling aids only)
+LIB_PATH = os.environ.get("DCD_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdcd_b200.so")
 
 # name -> (restype, argtypes); mirrors include/dcd_b200.h line by line
 SIGNATURES = {
@@ -24,6 +25,8 @@ SIGNATURES = {
     "dcd_edge_select_fwd": (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 5),
     "dcd_edge_solve_bwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_float, c_int, c_void_p, c_int] + [c_void_p] * 5),
     "dcd_dgde_locate_fwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dcd_dgde_frame_fwd": (c_int, [c_void_p] * 3 + [c_int64] + [c_int] * 6 + [c_void_p] * 4 + [c_int64, c_int, c_float, c_float, c_int, c_float]
+                           + [c_void_p] * 5),
     "dcd_dgde_depth_ensemble_fwd": (c_int, [c_void_p] * 7 + [c_int64, c_float, c_float, c_float, c_float] + [c_void_p] * 6),
     "dcd_poi_gather_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "dcd_gmw_ray_rescale_fwd": (c_int, [c_void_p] * 3 + [c_int64, c_void_p, c_void_p]),

@@ -31,30 +31,36 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into one shared library; returns its path."""
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) -> str:
+    """Compile every CUDA source into one shared library; returns its path.  `out` / `extra` build a variant (e.g. the
+    in-kernel trace build, extra=["-DDCD_FUSED_TRACE"]) next to the product library without touching it."""
+    variant = out != LIB
+    if not force and not variant and not _stale():
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", os.path.basename(out).replace(".so", "") if variant else "")
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("DCD_B200_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + os.environ.get("DCD_B200_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write("[%s]\n%s\n" % (src, out))
+            sys.stderr.write("[%s]\n%s\n" % (src, log))
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libdcd_b200.so")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--trace" in sys.argv:       # debug variant with the in-kernel timeline of the fused forward (profiles/trace_fused.py)
+        print(build_library(force=True, out=os.path.join(HERE, "libdcd_b200_trace.so"), extra=["-DDCD_FUSED_TRACE"]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -17,6 +17,8 @@ int launch_gmw_weights_fwd(const float*, const float*, const float*, const float
                            float*, float*, float*, cudaStream_t);
 int launch_dgde_locate(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                        const float*, const float*, int64_t, int, float, float, int, float, float*, float*, cudaStream_t);
+int launch_dgde_frame(const float*, const int64_t*, const int32_t*, int, int, int, int, int, int, const float*, const float*,
+                      const float*, const float*, int64_t, int, float, float, int, float, float*, float*, float*, float*, cudaStream_t);
 int launch_dgde_depth_ensemble(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                                int64_t, float, float, float, float, float*, float*, float*, int64_t*, float*, cudaStream_t);
 int launch_gmw_ray_rescale(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
@@ -108,6 +110,20 @@ int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* 
     if (kpts_off ? (!kps3d || !rot) : !depth_in) return DCD_E_INVALID;
     return launch_dgde_locate(kpts_off, kps3d, rot, K, points, offsets, pad, dims, depth_in, N, kpts_off ? n : 2, lo, hi, flags,
                               down_ratio, depth_out, locations, (cudaStream_t)stream);
+}
+
+int dcd_dgde_frame_fwd(const float* feature_maps, const int64_t* index, const int32_t* batch_idx, int64_t B, int C, int H, int W,
+                       int ch_kpts2d, int ch_kpts3d, int ch_offset3d, const float* rot, const float* K, const float* pad,
+                       const float* dims, int64_t N, int n, float lo, float hi, int flags, float down_ratio, float* depth_out,
+                       float* locations, float* kpts_img_out, float* kps3d_out, void* stream) {
+    if (N < 0 || B < 1 || C < 1 || H < 1 || W < 1 || bad_n(n)) return DCD_E_INVALID;
+    if (ch_kpts2d < 0 || ch_kpts2d + 2 * n > C || ch_kpts3d < 0 || ch_kpts3d + 3 * n > C || ch_offset3d < 0 || ch_offset3d + 2 > C)
+        return DCD_E_INVALID;
+    if (N == 0) return DCD_OK;
+    if (!feature_maps || !index || !rot || !K || !pad || (!depth_out && !locations)) return DCD_E_INVALID;
+    if (B > 1 && !batch_idx) return DCD_E_INVALID;
+    return launch_dgde_frame(feature_maps, index, batch_idx, C, H, W, ch_kpts2d, ch_kpts3d, ch_offset3d, rot, K, pad, dims, N, n, lo,
+                             hi, flags, down_ratio, depth_out, locations, kpts_img_out, kps3d_out, (cudaStream_t)stream);
 }
 
 int dcd_dgde_depth_ensemble_fwd(const float* kp10, const float* dims, const float* K, const float* direct,

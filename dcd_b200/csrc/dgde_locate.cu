@@ -87,7 +87,112 @@ dgde_locate_warp_kernel(const float* __restrict__ kpts_off, const float* __restr
     }
 }
 
+// The same epilogue reading the detector's regression map directly (row N2 fused into the load stage): for detection d at
+// heat-map position index[d] of image batch_idx[d] the keypoint offsets, 3D template points and the sub-pixel offset are
+// the values of their channel groups at that position of the [B,C,H,W] map (select_point_of_interest,
+// DGDE/model/layers/utils.py:120-145, + the key2channel slices of detector_infer.py:133,216,219), so POI gather ->
+// image keypoints -> edge solve -> mean -> location is ONE launch and the [B,K,C] gather never exists in memory.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+dgde_frame_warp_kernel(const float* __restrict__ fmap, const int64_t* __restrict__ index, const int32_t* __restrict__ batch_idx,
+                       int C, int H, int W, int ch_k2, int ch_k3, int ch_off,
+                       const float* __restrict__ rot, const float* __restrict__ K, const float* __restrict__ pad,
+                       const float* __restrict__ dims, int64_t N, int n, float lo, float hi, int flags, float down_ratio,
+                       float* __restrict__ depth_out, float* __restrict__ loc_out, float* __restrict__ kimg_out,
+                       float* __restrict__ k3_out) {
+    constexpr int NWARP = THREADS / 32;
+    const int E = n * (n - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* kp_all = reinterpret_cast<float4*>(smem_raw);                     // [NWARP][n]
+    uint32_t* tab_s = reinterpret_cast<uint32_t*>(kp_all + NWARP * n);        // [E]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < E; e += THREADS) {
+        int i, j;
+        decode_edge(e, n, i, j);
+        tab_s[e] = (uint32_t)(i * 16) | ((uint32_t)(j * 16) << 16);
+    }
+    __syncthreads();
+    float4* kp = kp_all + warp * n;
+    const unsigned char* kpb = reinterpret_cast<const unsigned char*>(kp);
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    const int64_t HW = (int64_t)H * W;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int64_t obj = (int64_t)blockIdx.x * NWARP + warp; obj < N; obj += (int64_t)gridDim.x * NWARP) {
+        const int64_t pos = index[obj];
+        const bool inside = pos >= 0 && pos < HW;             // like dcd_poi_gather_fwd: NaN instead of a fault
+        const float* base = fmap + (int64_t)(batch_idx != nullptr ? batch_idx[obj] : 0) * C * HW + (inside ? pos : 0);
+        auto chan = [&](int c) { return inside ? __ldg(base + (int64_t)c * HW) : qnan; };
+        const float* Ko = K + obj * 12;
+        const float f_u = __ldg(Ko + 0), c_u = __ldg(Ko + 2), f_v = __ldg(Ko + 5), c_v = __ldg(Ko + 6);
+        const float px = (float)(pos % W), py = (float)(pos / W);             // select_topk: xs = ind % W, ys = ind // W
+        const float cx = __fadd_rn(px, chan(ch_off)), cyy = __fadd_rn(py, chan(ch_off + 1));
+        const float pad_u = __ldg(pad + obj * 2), pad_v = __ldg(pad + obj * 2 + 1);
+        const float b3 = (flags & DCD_SUB_B3) ? __ldg(Ko + 11) : 0.f;
+        const float r = __ldg(rot + obj);
+        const float sn = sinf(r), cs = cosf(r);
+        for (int t = lane; t < n; t += 32) {
+            const float off_v = chan(ch_k2 + 2 * t + 1);
+            const float v_img = __fsub_rn(__fmul_rn(__fadd_rn(off_v, cyy), down_ratio), pad_v);
+            const float X = chan(ch_k3 + 3 * t), Y = chan(ch_k3 + 3 * t + 1), Z = chan(ch_k3 + 3 * t + 2);
+            kp[t] = keypoint_terms(v_img, X, Y, Z, sn, cs, normalise, c_v, f_v);
+            if (kimg_out != nullptr) {
+                const float u_img = __fsub_rn(__fmul_rn(__fadd_rn(chan(ch_k2 + 2 * t), cx), down_ratio), pad_u);
+                kimg_out[(obj * n + t) * 2] = u_img;
+                kimg_out[(obj * n + t) * 2 + 1] = v_img;
+            }
+            if (k3_out != nullptr) {
+                float* o = k3_out + (obj * n + t) * 3;
+                o[0] = X; o[1] = Y; o[2] = Z;
+            }
+        }
+        __syncwarp();
+        float acc = 0.f;
+        for (int e = lane; e < E; e += 32) {
+            const uint32_t p = tab_s[e];
+            const float4 a = *reinterpret_cast<const float4*>(kpb + (p & 0xffffu));
+            const float4 b = *reinterpret_cast<const float4*>(kpb + (p >> 16));
+            acc += edge_depth(a, b, lo, hi, b3);
+        }
+        acc = warp_sum(acc);
+        const float depth = __fdiv_rn(acc, (float)E);
+        __syncwarp();
+        if (lane == 0) {
+            if (depth_out != nullptr) depth_out[obj] = depth;
+            if (loc_out != nullptr) {
+                const float u = __fsub_rn(__fmul_rn(cx, down_ratio), pad_u);
+                const float v = __fsub_rn(__fmul_rn(cyy, down_ratio), pad_v);
+                const float b_x = __fdiv_rn(__ldg(Ko + 3), -f_u), b_y = __fdiv_rn(__ldg(Ko + 7), -f_v);
+                float x = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(u, c_u), depth), f_u), b_x);
+                float y = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(v, c_v), depth), f_v), b_y);
+                if (dims != nullptr) y = __fadd_rn(y, __fmul_rn(__ldg(dims + obj * 3 + 1), 0.5f));
+                loc_out[obj * 3 + 0] = x;
+                loc_out[obj * 3 + 1] = y;
+                loc_out[obj * 3 + 2] = depth;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+int launch_dgde_frame(const float* fmap, const int64_t* index, const int32_t* batch_idx, int C, int H, int W, int ch_k2, int ch_k3,
+                      int ch_off, const float* rot, const float* K, const float* pad, const float* dims, int64_t N, int n, float lo,
+                      float hi, int flags, float down_ratio, float* depth_out, float* loc_out, float* kimg_out, float* k3_out,
+                      cudaStream_t st) {
+    constexpr int T = 128;                                  // a frame has <= 50 detections: more, smaller CTAs
+    const int E = n * (n - 1) / 2;
+    const size_t smem = (size_t)(T / 32) * n * sizeof(float4) + (size_t)E * sizeof(uint32_t);
+    if (smem > 227 * 1024) return DCD_E_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(dgde_frame_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t want = (N + T / 32 - 1) / (T / 32);
+    const int64_t cap = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    dgde_frame_warp_kernel<T><<<grid, T, smem, st>>>(fmap, index, batch_idx, C, H, W, ch_k2, ch_k3, ch_off, rot, K, pad, dims, N, n,
+                                                     lo, hi, flags, down_ratio, depth_out, loc_out, kimg_out, k3_out);
+    DCD_CHECK_LAUNCH();
+    return DCD_OK;
+}
 
 int launch_dgde_locate(const float* kpts_off, const float* kps3d, const float* rot, const float* K, const float* points,
                        const float* offsets, const float* pad, const float* dims, const float* depth_in, int64_t N, int n,

@@ -7,7 +7,7 @@
 //      sorts first, as in torch.topk), rows of the upper triangle spread over the warps, lanes along j;
 //   2. radix select: four 8-bit histogram passes (MSB first) find the k-th largest key T and how many edges
 //      equal to T belong to the selection; an ORDERED compaction (warp ballots, edge id order) collects the
-//      edges above T and the first ties at T as 64-bit composites  key << 32 | ~id  — so only k <= 2048 of the E
+//      edges above T and the first ties at T as (key, ~id) pairs  — so only k <= 2048 of the E
 //      (2628 ... 32 640) candidates are ever sorted;
 //   3. bitonic sort of the 2048-padded composites with 8 elements per thread IN REGISTERS: strides 1-4 are register
 //      compare-exchanges, strides 8-128 warp shuffles, strides 256-1024 register compare-exchanges again after a
@@ -38,45 +38,108 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool vali
     if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
 }
 
-// compare-exchange inside a thread: afterwards `a` holds the element that belongs to the lower index
-__device__ __forceinline__ void ce_reg(unsigned long long& a, unsigned long long& b, bool desc) {
-    const bool swap = desc ? (a < b) : (a > b);
-    const unsigned long long t = a;
-    a = swap ? b : a;
-    b = swap ? t : b;
+// A sort element is the pair (key, ~edge id) held as two 32-bit registers; elements are distinct (unique ids) except for the
+// all-zero padding, so "not less" can stand for "greater" and every exchange is branch-free predicate logic + selects
+// (written on 64-bit integers the compiler turned each exchange into divergent branches).
+struct SortRegs {
+    uint32_t k[SEL_EPT];     // key bits
+    uint32_t v[SEL_EPT];     // 0xffffffff - edge id (larger = earlier edge)
+};
+__device__ __forceinline__ bool elem_less(uint32_t ka, uint32_t va, uint32_t kb, uint32_t vb) {
+    return (ka < kb) | ((ka == kb) & (va < vb));
+}
+// compare-exchange inside a thread: afterwards slot a (the lower index) holds the larger element iff desc
+__device__ __forceinline__ void ce_reg(SortRegs& x, int a, int b, bool desc) {
+    const bool swap = elem_less(x.k[a], x.v[a], x.k[b], x.v[b]) == desc;
+    const uint32_t ka = x.k[a], va = x.v[a], kb = x.k[b], vb = x.v[b];
+    x.k[a] = swap ? kb : ka;
+    x.v[a] = swap ? vb : va;
+    x.k[b] = swap ? ka : kb;
+    x.v[b] = swap ? va : vb;
 }
 
-// strides 4, 2, 1 of a merge step on the thread's 8 consecutive elements (layout A: idx = 8 t + r)
-__device__ __forceinline__ void merge_regs_A(unsigned long long (&x)[SEL_EPT], int base_idx, int size, int from_stride) {
+// Everything below is indexed by compile-time constants (SIZE / FROM are template parameters) so that the 8 elements of a
+// thread stay in registers and every compare-exchange is straight-line code.
+
+// strides min(4, FROM), ..., 1 of the merge step SIZE on the thread's 8 consecutive elements (layout A: idx = 8 t + r)
+template <int SIZE, int FROM>
+__device__ __forceinline__ void merge_regs_A(SortRegs& x, int base_idx) {
 #pragma unroll
     for (int stride = 4; stride >= 1; stride >>= 1) {
-        if (stride > from_stride) continue;
+        if (stride <= FROM) {
 #pragma unroll
-        for (int r = 0; r < SEL_EPT; ++r) {
-            if ((r & stride) == 0) {
-                const bool desc = ((base_idx + r) & size) == 0;
-                ce_reg(x[r], x[r + stride], desc);
+            for (int r = 0; r < SEL_EPT; ++r) {
+                if ((r & stride) == 0) {
+                    const bool desc = ((base_idx + r) & SIZE) == 0;
+                    ce_reg(x, r, r + stride, desc);
+                }
             }
         }
     }
 }
 
-// strides 8 .. 128 of a merge step through warp shuffles (layout A: lane bit m <-> stride 8 << m)
-__device__ __forceinline__ void merge_shfl_A(unsigned long long (&x)[SEL_EPT], int base_idx, int size, int from_stride, int lane) {
+// strides min(128, FROM), ..., 8 of the merge step SIZE through warp shuffles (layout A: lane bit m <-> stride 8 << m)
+template <int SIZE, int FROM>
+__device__ __forceinline__ void merge_shfl_A(SortRegs& x, int base_idx, int lane) {
 #pragma unroll
     for (int m = 4; m >= 0; --m) {
-        const int stride = 8 << m;
-        if (stride > from_stride) continue;
-        const bool lower = (lane & (1 << m)) == 0;
+        if ((8 << m) <= FROM) {
+            const bool lower = (lane & (1 << m)) == 0;
 #pragma unroll
-        for (int r = 0; r < SEL_EPT; ++r) {
-            const unsigned long long p = __shfl_xor_sync(0xffffffffu, x[r], 1 << m);
-            const bool desc = ((base_idx + r) & size) == 0;
-            const bool want_max = lower == desc;
-            const bool take = want_max ? (p > x[r]) : (p < x[r]);
-            x[r] = take ? p : x[r];
+            for (int r = 0; r < SEL_EPT; ++r) {
+                const uint32_t pk = __shfl_xor_sync(0xffffffffu, x.k[r], 1 << m), pv = __shfl_xor_sync(0xffffffffu, x.v[r], 1 << m);
+                const bool desc = ((base_idx + r) & SIZE) == 0;
+                const bool want_max = lower == desc;
+                const bool take = elem_less(x.k[r], x.v[r], pk, pv) == want_max;      // the partner makes the mirrored choice
+                x.k[r] = take ? pk : x.k[r];
+                x.v[r] = take ? pv : x.v[r];
+            }
         }
     }
+}
+
+// strides SIZE / 2, ..., 256 of the merge step SIZE on layout B (idx = 256 r + t): the stride is a register distance
+template <int SIZE>
+__device__ __forceinline__ void merge_regs_B(SortRegs& x, int tid) {
+#pragma unroll
+    for (int rs = SEL_EPT / 2; rs >= 1; rs >>= 1) {
+        if (rs * SEL_THREADS <= SIZE / 2) {
+#pragma unroll
+            for (int r = 0; r < SEL_EPT; ++r) {
+                if ((r & rs) == 0) {
+                    const bool desc = ((r * SEL_THREADS + tid) & SIZE) == 0;
+                    ce_reg(x, r, r + rs, desc);
+                }
+            }
+        }
+    }
+}
+
+// one merge step of size SIZE >= 512: transpose to layout B through shared memory, exchange in registers, transpose back
+template <int SIZE>
+__device__ __forceinline__ void merge_big(SortRegs& x, uint2* buf_s, int tid, int lane) {
+    const int baseA = tid * SEL_EPT;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(baseA + r)] = make_uint2(x.v[r], x.k[r]);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SEL_EPT; ++r) { const uint2 e = buf_s[sel_phys(r * SEL_THREADS + tid)]; x.v[r] = e.x; x.k[r] = e.y; }
+    merge_regs_B<SIZE>(x, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(r * SEL_THREADS + tid)] = make_uint2(x.v[r], x.k[r]);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SEL_EPT; ++r) { const uint2 e = buf_s[sel_phys(baseA + r)]; x.v[r] = e.x; x.k[r] = e.y; }
+    merge_shfl_A<SIZE, 128>(x, baseA, lane);
+    merge_regs_A<SIZE, 4>(x, baseA);
+}
+
+template <int SIZE>
+__device__ __forceinline__ void merge_warp(SortRegs& x, int baseA, int lane) {
+    merge_shfl_A<SIZE, SIZE / 2>(x, baseA, lane);
+    merge_regs_A<SIZE, 4>(x, baseA);
 }
 
 template <int THREADS>
@@ -90,7 +153,7 @@ edge_select_radix_kernel(const float* __restrict__ kps, const float* __restrict_
     static_assert(THREADS == SEL_THREADS, "layout constants assume 256 threads");
     const int E = n * (n - 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* buf_s = reinterpret_cast<unsigned long long*>(smem_raw);           // [SEL_BUF]
+    uint2* buf_s = reinterpret_cast<uint2*>(smem_raw);                                     // [SEL_BUF] (.x = ~id, .y = key)
     float4* kp_s = reinterpret_cast<float4*>(buf_s + SEL_BUF);                             // [n] {v, Y, vC, C}
     float* v_s = reinterpret_cast<float*>(kp_s + n);                                       // [n]
     uint32_t* hist_s = reinterpret_cast<uint32_t*>(v_s + ((n + 3) & ~3));                  // [256]
@@ -201,7 +264,7 @@ edge_select_radix_kernel(const float* __restrict__ kps, const float* __restrict_
             }
             if (lane == 0) { misc_s[2 + warp] = ngt; misc_s[2 + SEL_WARPS + warp] = neq; }
         }
-        for (int q = tid; q < SEL_P - k; q += THREADS) buf_s[sel_phys(k + q)] = 0ull;      // padding sorts last
+        for (int q = tid; q < SEL_P - k; q += THREADS) buf_s[sel_phys(k + q)] = make_uint2(0u, 0u);     // padding sorts last
         __syncthreads();
         {
             uint32_t gt_off = 0u, eq_off = 0u;
@@ -213,7 +276,7 @@ edge_select_radix_kernel(const float* __restrict__ kps, const float* __restrict_
                 const uint32_t key = e < w_hi ? key_s[e] : 0u;
                 const bool gt = e < w_hi && key > T, eq = e < w_hi && key == T;
                 const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
-                const unsigned long long comp = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);
+                const uint2 comp = make_uint2(0xffffffffu - (uint32_t)e, key);
                 if (gt) buf_s[sel_phys((int)(gt_off + __popc(bg & lt_mask)))] = comp;
                 if (eq) {
                     const uint32_t rnk = eq_off + __popc(be & lt_mask);
@@ -225,55 +288,32 @@ edge_select_radix_kernel(const float* __restrict__ kps, const float* __restrict_
         }
         __syncthreads();
         // ---- phase 3: bitonic sort (descending) of SEL_P composites, 8 per thread in registers
-        unsigned long long x[SEL_EPT];
+        SortRegs x;
         const int baseA = tid * SEL_EPT;                     // layout A: idx = 8 t + r
 #pragma unroll
-        for (int r = 0; r < SEL_EPT; ++r) x[r] = buf_s[sel_phys(r * THREADS + tid)];       // any bijection will do for unsorted input
-#pragma unroll
-        for (int size = 2; size <= 8; size <<= 1) merge_regs_A(x, baseA, size, size >> 1);
-#pragma unroll
-        for (int size = 16; size <= 256; size <<= 1) {
-            merge_shfl_A(x, baseA, size, size >> 1, lane);
-            merge_regs_A(x, baseA, size, 4);
+        for (int r = 0; r < SEL_EPT; ++r) {                  // any bijection will do for unsorted input
+            const uint2 e = buf_s[sel_phys(r * THREADS + tid)];
+            x.v[r] = e.x; x.k[r] = e.y;
         }
-#pragma unroll
-        for (int size = 512; size <= SEL_P; size <<= 1) {
-            // strides >= 256 live in the warp index: transpose to layout B (idx = 256 r + t), exchange in registers, transpose back
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(baseA + r)] = x[r];
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < SEL_EPT; ++r) x[r] = buf_s[sel_phys(r * THREADS + tid)];
-#pragma unroll
-            for (int stride = SEL_P / 2; stride >= THREADS; stride >>= 1) {
-                if (stride > (size >> 1)) continue;
-                const int rs = stride / THREADS;
-#pragma unroll
-                for (int r = 0; r < SEL_EPT; ++r) {
-                    if ((r & rs) == 0) {
-                        const bool desc = (((r * THREADS + tid)) & size) == 0;
-                        ce_reg(x[r], x[r + rs], desc);
-                    }
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(r * THREADS + tid)] = x[r];
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < SEL_EPT; ++r) x[r] = buf_s[sel_phys(baseA + r)];
-            merge_shfl_A(x, baseA, size, 128, lane);
-            merge_regs_A(x, baseA, size, 4);
-        }
+        merge_regs_A<2, 1>(x, baseA);
+        merge_regs_A<4, 2>(x, baseA);
+        merge_regs_A<8, 4>(x, baseA);
+        merge_warp<16>(x, baseA, lane);
+        merge_warp<32>(x, baseA, lane);
+        merge_warp<64>(x, baseA, lane);
+        merge_warp<128>(x, baseA, lane);
+        merge_warp<256>(x, baseA, lane);
+        merge_big<512>(x, buf_s, tid, lane);
+        merge_big<1024>(x, buf_s, tid, lane);
+        merge_big<2048>(x, buf_s, tid, lane);
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(baseA + r)] = x[r];
+        for (int r = 0; r < SEL_EPT; ++r) buf_s[sel_phys(baseA + r)] = make_uint2(x.v[r], x.k[r]);
         __syncthreads();
         // ---- outputs for the k winners
         float acc = 0.f;
         for (int r = tid; r < k; r += THREADS) {
-            const int e = (int)(0xffffffffu - (uint32_t)(buf_s[sel_phys(r)] & 0xffffffffull));
+            const int e = (int)(0xffffffffu - buf_s[sel_phys(r)].x);
             idx_out[obj * k + r] = (int64_t)e;
             if (depth_sel != nullptr || mask_sel != nullptr || depth_mean != nullptr) {
                 int i, j;

@@ -384,6 +384,192 @@ edge_mean_group_kernel(const float* __restrict__ kps, const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward, mean only, throughput variant for n = 1 (mod 4) keypoints (the reference's n = 73): register blocking on
+// top of the circulant enumeration.  ncu on the kernel above (profiles/r02_edge_mean.md): 3 LDS.32 per edge keep the
+// LSU at 55-66 % and, with ~4 warps per scheduler and one dependent chain per edge pair, the warps mostly wait on
+// fixed-latency dependencies.  Here a lane OWNS 4 CONSECUTIVE keypoints i0 .. i0+3 (12 terms in registers) and walks
+// the 39 partners i0+1 .. i0+39: every loaded partner serves up to four edges (0.8 LDS.32 per edge instead of 3) and
+// the four edges are independent chains (4x the instruction-level parallelism).  Which (own, partner) combinations
+// are circulant pairs (1 <= offset <= (n-1)/2) is a compile-time pattern, the same for every lane, so nothing is
+// masked at run time: per lane 70 packed pairs + 4 single edges.  The (n-1)/4 lanes of an object cover keypoints
+// 0 .. n-2; the last keypoint's (n-1)/2 edges (partners 0 .. (n-1)/2-1) are dealt two per lane.  Keypoint terms are
+// stored interleaved by (index mod 4) so that consecutive lanes read consecutive words for every partner, and the
+// per-object stride is congruent to the lanes per object modulo 32: conflict-free across the objects of a group.
+// Every edge value is still bit-identical to the reference's; sum order per object is fixed (deterministic,
+// independent of the group an object falls into).
+// ---------------------------------------------------------------------------------------------
+template <int NK>
+struct BlkGeom {
+    static_assert(NK % 4 == 1 && NK >= 9, "the blocked kernel needs n = 1 (mod 4)");
+    static constexpr int LPO = (NK - 1) / 4;                 // lanes per object (18)
+    static constexpr int D = (NK - 1) / 2;                   // circulant offsets 1 .. D (36)
+    static constexpr int NPART = D + 3;                      // partners i0+1 .. i0+NPART of a lane's four keypoints (39)
+    static constexpr int S4 = (4 * (LPO - 1) + NPART) / 4 + 1;                        // entries per residue class (27)
+    static constexpr int OS = 4 * S4 + ((LPO - 4 * S4) % 32 + 32) % 32;               // object stride == LPO (mod 32) (114)
+    static constexpr int NDUP = 4 * (LPO - 1) + NPART - NK + 1;                       // keypoints repeated after the n-th (35)
+};
+template <int NK, int G>
+__host__ __device__ constexpr int blk_warp_floats() { return 3 * G * BlkGeom<NK>::OS + ((G * BlkGeom<NK>::LPO + 31) & ~31) + 8 * G; }
+
+template <int NK, int G, bool FAST>
+__global__ void __launch_bounds__(GRP_WARPS * 32)
+edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ kps3d,
+                       const float* __restrict__ rot, const float* __restrict__ K,
+                       int64_t N, float lo, float hi, int flags, float* __restrict__ depth_mean) {
+    using Gm = BlkGeom<NK>;
+    constexpr int LPO = Gm::LPO, D = Gm::D, NPART = Gm::NPART, S4 = Gm::S4, OS = Gm::OS;
+    constexpr int E = NK * (NK - 1) / 2;
+    extern __shared__ __align__(16) float blk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* v_s = blk_smem + (size_t)warp * blk_warp_floats<NK, G>();
+    float* Y_s = v_s + G * OS;
+    float* c_s = Y_s + G * OS;
+    float* part_s = c_s + G * OS;                            // [G * LPO] per-lane sums
+    float* sc_s = part_s + ((G * LPO + 31) & ~31);           // [5][G]: sin, cos, cy, fy, b3
+    const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
+    const int64_t ngroups = (N + G - 1) / G;
+    auto pos = [](int e) { return (e & 3) * S4 + (e >> 2); };   // interleaved position of element e inside an object
+
+    for (int64_t grp = (int64_t)blockIdx.x * GRP_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * GRP_WARPS) {
+        const int64_t obj0 = grp * G;
+        const int gcount = (int)((N - obj0 < G) ? N - obj0 : G);
+        if (lane < gcount) {
+            const int64_t obj = obj0 + lane;
+            float cy = 0.f, fy = 1.f, b3 = 0.f;
+            if (K != nullptr) {
+                const float* Ko = K + obj * 12;
+                if (normalise) { cy = __ldg(Ko + 6); fy = __ldg(Ko + 5); }
+                if (flags & DCD_SUB_B3) b3 = __ldg(Ko + 11);
+            }
+            const float r = __ldg(rot + obj);
+            sc_s[lane] = sinf(r);
+            sc_s[G + lane] = cosf(r);
+            sc_s[2 * G + lane] = cy;
+            sc_s[3 * G + lane] = fy;
+            sc_s[4 * G + lane] = b3;
+        }
+        __syncwarp();
+        // ---- stage the group's keypoint terms (global keypoint index = obj0 * NK + slot: coalesced)
+        bool bad = false;
+        const int slots = gcount * NK;
+        const float* kv = kps + obj0 * NK * 2 + 1;
+        const float* k3 = kps3d + obj0 * NK * 3;
+#pragma unroll 4
+        for (int s0 = 0; s0 < slots; s0 += 32) {
+            const int s = s0 + lane;
+            if (s < slots) {
+                const int g = s / NK, i = s - g * NK;
+                const float4 t = keypoint_terms(__ldg(kv + 2 * s), __ldg(k3 + 3 * s), __ldg(k3 + 3 * s + 1), __ldg(k3 + 3 * s + 2),
+                                                sc_s[g], sc_s[G + g], normalise, sc_s[2 * G + g], sc_s[3 * G + g]);
+                const int p = g * OS + pos(i);
+                v_s[p] = t.x; Y_s[p] = t.y; c_s[p] = t.z;
+                if (i < Gm::NDUP) {
+                    const int p2 = g * OS + pos(i + NK);
+                    v_s[p2] = t.x; Y_s[p2] = t.y; c_s[p2] = t.z;
+                }
+                bad |= !(fabsf(t.x) + fabsf(t.y) + fabsf(t.z) <= 3.0e38f);
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        __syncwarp();
+        // ---- edges: lane = (object g, quad q), keypoints 4q .. 4q+3
+        const int lanes = gcount * LPO;
+        for (int L0 = 0; L0 < lanes; L0 += 32) {
+            const int L = L0 + lane;
+            const bool active = L < lanes;
+            const int g = active ? L / LPO : 0, q = active ? L - g * LPO : 0;
+            const float* pv = v_s + g * OS + q;              // element 4q + t sits at pv[(t & 3) * S4 + (t >> 2)]
+            const float* pY = pv + G * OS;
+            const float* pc = pY + G * OS;
+            float total;
+            if (!bad) {
+                float2 ov[4], oY[4], oc[4];                  // own terms, duplicated into both halves of a packed pair
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float x = pv[a * S4], y = pY[a * S4], z = pc[a * S4];
+                    ov[a] = make_float2(x, x); oY[a] = make_float2(y, y); oc[a] = make_float2(z, z);
+                }
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+                float accs = 0.f;
+#pragma unroll
+                for (int tp = 1; tp <= NPART; tp += 2) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const bool has1 = tp + 1 <= NPART;
+                    const int o0 = (tp & 3) * S4 + (tp >> 2), o1 = has1 ? ((tp + 1) & 3) * S4 + ((tp + 1) >> 2) : o0;
+                    const float2 vj = make_float2(pv[o0], pv[o1]), Yj = make_float2(pY[o0], pY[o1]), cj = make_float2(pc[o0], pc[o1]);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int d0 = tp - a, d1 = tp + 1 - a;
+                        const bool ok0 = d0 >= 1 && d0 <= D, ok1 = has1 && d1 >= 1 && d1 <= D;
+                        if (ok0 && ok1) {
+                            const float2 z = FAST ? edge_quotient_fast2(ov[a], oY[a], oc[a], vj, Yj, cj, lo, hi)
+                                                  : edge_quotient_finite2(ov[a], oY[a], oc[a], vj, Yj, cj, lo, hi);
+                            if (a & 1) acc1 = add2_rn(acc1, z); else acc0 = add2_rn(acc0, z);
+                        } else if (ok0) {
+                            accs += FAST ? edge_quotient_fast(ov[a].x, oY[a].x, oc[a].x, vj.x, Yj.x, cj.x, lo, hi)
+                                         : edge_quotient_finite(ov[a].x, oY[a].x, oc[a].x, vj.x, Yj.x, cj.x, lo, hi);
+                        } else if (ok1) {
+                            accs += FAST ? edge_quotient_fast(ov[a].x, oY[a].x, oc[a].x, vj.y, Yj.y, cj.y, lo, hi)
+                                         : edge_quotient_finite(ov[a].x, oY[a].x, oc[a].x, vj.y, Yj.y, cj.y, lo, hi);
+                        }
+                    }
+                }
+                // the last keypoint (NK - 1) against partners 2q, 2q + 1
+                {
+                    const float* bv = v_s + g * OS;
+                    const float* bY = bv + G * OS;
+                    const float* bc = bY + G * OS;
+                    constexpr int pl = ((NK - 1) & 3) * S4 + ((NK - 1) >> 2);
+                    const int e0 = 2 * q, e1 = 2 * q + 1;
+                    const int p0 = (e0 & 3) * S4 + (e0 >> 2), p1 = (e1 & 3) * S4 + (e1 >> 2);
+                    const float xl = bv[pl], yl = bY[pl], zl = bc[pl];
+                    const float2 z = FAST ? edge_quotient_fast2(make_float2(xl, xl), make_float2(yl, yl), make_float2(zl, zl),
+                                                                make_float2(bv[p0], bv[p1]), make_float2(bY[p0], bY[p1]),
+                                                                make_float2(bc[p0], bc[p1]), lo, hi)
+                                          : edge_quotient_finite2(make_float2(xl, xl), make_float2(yl, yl), make_float2(zl, zl),
+                                                                  make_float2(bv[p0], bv[p1]), make_float2(bY[p0], bY[p1]),
+                                                                  make_float2(bc[p0], bc[p1]), lo, hi);
+                    acc0 = add2_rn(acc0, z);
+                }
+                total = ((acc0.x + acc0.y) + (acc1.x + acc1.y)) + accs;
+            } else {
+                // non-finite terms somewhere in the group: the same edges with torch's NaN-propagating clamps
+                const float* bv = v_s + g * OS;
+                const float* bY = bv + G * OS;
+                const float* bc = bY + G * OS;
+                float acc = 0.f;
+#pragma unroll 1
+                for (int a = 0; a < 4; ++a) {
+                    const int pa = pos(4 * q + a);
+#pragma unroll 1
+                    for (int d = 1; d <= D; ++d) {
+                        const int pb = pos(4 * q + a + d);
+                        acc += edge_quotient_ieee(bv[pa], bY[pa], bc[pa], bv[pb], bY[pb], bc[pb], lo, hi);
+                    }
+                }
+                const int pl = pos(NK - 1);
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    const int pb = pos(2 * q + k);
+                    acc += edge_quotient_ieee(bv[pl], bY[pl], bc[pl], bv[pb], bY[pb], bc[pb], lo, hi);
+                }
+                total = acc;
+            }
+            if (active) part_s[L] = total;
+        }
+        __syncwarp();
+        // ---- per-object mean: the LPO lane sums of an object in fixed order
+        if (lane < gcount) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < LPO; ++k) t += part_s[lane * LPO + k];
+            depth_mean[obj0 + lane] = __fsub_rn(__fdiv_rn(t, (float)E), sc_s[4 * G + lane]);
+        }
+        __syncwarp();                                        // all lanes done with the group's arrays before restaging
+    }
+}
+
 // objects per group: the G in 1..8 that fills the warps of a group best within ~12 KB of shared memory per warp
 int grp_pick_G(int n) {
     int best = 1;
@@ -604,6 +790,22 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
                                                                                       depth_mean);                           \
     } while (0)
         if (n == 73) {
+            // n = 1 (mod 4): the register-blocked kernel, 7 objects (126 lanes) per warp group
+            constexpr int BG = 7;
+            const size_t bsmem = (size_t)GRP_WARPS * blk_warp_floats<73, BG>() * sizeof(float);
+            const int64_t bgroups = (N + BG - 1) / BG, bwant = (bgroups + GRP_WARPS - 1) / GRP_WARPS;
+            int bper = (int)((227 * 1024) / (bsmem + 1024));
+            if (bper > 8) bper = 8;
+            const int64_t bcap = (int64_t)sms * bper;
+            const int bgrid = (int)(bwant < bcap ? bwant : bcap);
+            if (fast) {
+                cudaFuncSetAttribute(edge_mean_block_kernel<73, BG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+                edge_mean_block_kernel<73, BG, true><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean);
+            } else {
+                cudaFuncSetAttribute(edge_mean_block_kernel<73, BG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+                edge_mean_block_kernel<73, BG, false><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean);
+            }
+        } else if (false) {
             if (fast) DCD_LAUNCH_GRP(73, 7, true); else DCD_LAUNCH_GRP(73, 7, false);
         } else {
             if (fast) DCD_LAUNCH_GRP(0, 0, true); else DCD_LAUNCH_GRP(0, 0, false);

@@ -721,9 +721,10 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                         __stcs(reinterpret_cast<float4*>(G + col0 + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));   // streamed: keep the weight image in L2
                 }
             } else if (net == 0) {
-                // park the 4-d net's features in this CTA's slice of an L2-resident scratch ([ES/4][128] float4 like Xs): the
+                // park the 4-d net's features in this CTA's slice of an L2-resident scratch ([ES/4][128] float4 like Xs; the 8
+                // slices of a group fill exactly one object's worth of the workspace slot, EP = 8 ES): the
                 // thread that writes a word is the one that reads it back after the 6-d net, so no fence or barrier is needed
-                float4* Pk = park + ((size_t)blockIdx.x * (FES_MAX / 4)) * CH + ch;
+                float4* Pk = park + ((size_t)blockIdx.x * (ES / 4)) * CH + ch;
                 for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
                     float v[16];
                     final_unit(col0, v);
@@ -735,7 +736,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 // per edge the three channel sums |a|^2, |c|^2, a.c — 32 channels by a halving shuffle tree, the 4 lane quarters
                 // through shared memory (the operand buffers are idle here) — then
                 //   w = 1 / sqrt(max((|c^|^2 - 2 a^.c^) + |a^|^2, 1e-30)),  a^ = a / max(|a|, 1e-12)
-                const float4* Pk = park + ((size_t)blockIdx.x * (FES_MAX / 4)) * CH + ch;
+                const float4* Pk = park + ((size_t)blockIdx.x * (ES / 4)) * CH + ch;
                 float* red = reinterpret_cast<float*>(Bbuf) + wg * (2 * 4 * 48);      // [2 buffers][4 quarters][16 edges][3]
                 float* W = reg_w + obj * (int64_t)E + e_base;
                 int itn = 0;
@@ -749,9 +750,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float c = cv[4 * q4 + i];
-                            aa[4 * q4 + i] = av[i] * av[i];
-                            cc[4 * q4 + i] = c * c;
-                            ac[4 * q4 + i] = av[i] * c;
+                            aa[4 * q4 + i] = __fmul_rn(av[i], av[i]);          // (explicit roundings: gmw_edge_weight_kernel<true>
+                            cc[4 * q4 + i] = __fmul_rn(c, c);                  //  replays this exact sequence)
+                            ac[4 * q4 + i] = __fmul_rn(av[i], c);
                         }
                     }
                     // halving tree over the 32 lanes: afterwards lane l holds the sums of edge l >> 1
@@ -762,14 +763,14 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                         for (int k = 0; k < h; ++k) {
                             const float sa = up ? aa[k] : aa[k + h], sc = up ? cc[k] : cc[k + h], sx = up ? ac[k] : ac[k + h];
                             const float ka = up ? aa[k + h] : aa[k], kc = up ? cc[k + h] : cc[k], kx = up ? ac[k + h] : ac[k];
-                            aa[k] = ka + __shfl_xor_sync(0xffffffffu, sa, 2 * h);
-                            cc[k] = kc + __shfl_xor_sync(0xffffffffu, sc, 2 * h);
-                            ac[k] = kx + __shfl_xor_sync(0xffffffffu, sx, 2 * h);
+                            aa[k] = __fadd_rn(ka, __shfl_xor_sync(0xffffffffu, sa, 2 * h));
+                            cc[k] = __fadd_rn(kc, __shfl_xor_sync(0xffffffffu, sc, 2 * h));
+                            ac[k] = __fadd_rn(kx, __shfl_xor_sync(0xffffffffu, sx, 2 * h));
                         }
                     }
-                    aa[0] += __shfl_xor_sync(0xffffffffu, aa[0], 1);
-                    cc[0] += __shfl_xor_sync(0xffffffffu, cc[0], 1);
-                    ac[0] += __shfl_xor_sync(0xffffffffu, ac[0], 1);
+                    aa[0] = __fadd_rn(aa[0], __shfl_xor_sync(0xffffffffu, aa[0], 1));
+                    cc[0] = __fadd_rn(cc[0], __shfl_xor_sync(0xffffffffu, cc[0], 1));
+                    ac[0] = __fadd_rn(ac[0], __shfl_xor_sync(0xffffffffu, ac[0], 1));
                     float* rb = red + (itn & 1) * (4 * 48);
                     if ((lane & 1) == 0) {
                         float* o = rb + quarter * 48 + (lane >> 1) * 3;
@@ -780,11 +781,12 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                         const int e = col0 + lane;
                         if (e < valid) {
                             const float* o = rb + lane * 3;
-                            const float saa = (o[0] + o[48]) + (o[96] + o[144]);
-                            const float scc = (o[1] + o[49]) + (o[97] + o[145]);
-                            const float sac = (o[2] + o[50]) + (o[98] + o[146]);
+                            const float saa = __fadd_rn(__fadd_rn(o[0], o[48]), __fadd_rn(o[96], o[144]));
+                            const float scc = __fadd_rn(__fadd_rn(o[1], o[49]), __fadd_rn(o[97], o[145]));
+                            const float sac = __fadd_rn(__fadd_rn(o[2], o[50]), __fadd_rn(o[98], o[146]));
                             const float n4 = fmaxf(sqrtf(saa), 1e-12f), n6 = fmaxf(sqrtf(scc), 1e-12f);
-                            const float a2 = __fdiv_rn(saa, n4 * n4), c2 = __fdiv_rn(scc, n6 * n6), acn = __fdiv_rn(sac, n4 * n6);
+                            const float a2 = __fdiv_rn(saa, __fmul_rn(n4, n4)), c2 = __fdiv_rn(scc, __fmul_rn(n6, n6));
+                            const float acn = __fdiv_rn(sac, __fmul_rn(n4, n6));
                             const float s2 = __fadd_rn(__fadd_rn(c2, -2.f * acn), a2);
                             W[e] = __fdiv_rn(1.f, sqrtf(fmaxf(s2, 1e-30f)));
                         }

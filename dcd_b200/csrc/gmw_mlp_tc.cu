@@ -429,10 +429,48 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
         if (FINAL) return X[(int64_t)c * EP];
         return fmaxf((Y[(int64_t)c * EP] - s.x) * s.y, 0.f) + X[(int64_t)c * EP];
     };
+    if (FINAL) {
+        // Same arithmetic, in the same order, as the paired epilogue of mlp_fused_kernel (gmw_mlp_fused.cu): the three channel
+        // sums |a|^2, |c|^2, a.c per lane quarter by the halving tree (c, c^16), (.., c^8), ... then the four quarters, and the
+        // weight from the sums — so a batch gives bit-identical weights whichever of the two schedules its chunks take.
+        float saa = 0.f, scc = 0.f, sac = 0.f;
+        float qa[4], qc[4], qx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float ta[16], tc[16], tx[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int c0 = 32 * q + k, c1 = c0 + 16;
+                const float a0 = X4[(int64_t)c0 * EP], a1 = X4[(int64_t)c1 * EP], b0 = X6[(int64_t)c0 * EP], b1 = X6[(int64_t)c1 * EP];
+                if (feat4 != nullptr) { feat4[(obj * CH + c0) * (int64_t)E + e] = a0; feat4[(obj * CH + c1) * (int64_t)E + e] = a1; }
+                if (feat6 != nullptr) { feat6[(obj * CH + c0) * (int64_t)E + e] = b0; feat6[(obj * CH + c1) * (int64_t)E + e] = b1; }
+                ta[k] = __fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1));
+                tc[k] = __fadd_rn(__fmul_rn(b0, b0), __fmul_rn(b1, b1));
+                tx[k] = __fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+            }
+#pragma unroll
+            for (int h = 8; h >= 1; h >>= 1)
+#pragma unroll
+                for (int k = 0; k < h; ++k) {
+                    ta[k] = __fadd_rn(ta[k], ta[k + h]);
+                    tc[k] = __fadd_rn(tc[k], tc[k + h]);
+                    tx[k] = __fadd_rn(tx[k], tx[k + h]);
+                }
+            qa[q] = ta[0]; qc[q] = tc[0]; qx[q] = tx[0];
+        }
+        saa = __fadd_rn(__fadd_rn(qa[0], qa[1]), __fadd_rn(qa[2], qa[3]));
+        scc = __fadd_rn(__fadd_rn(qc[0], qc[1]), __fadd_rn(qc[2], qc[3]));
+        sac = __fadd_rn(__fadd_rn(qx[0], qx[1]), __fadd_rn(qx[2], qx[3]));
+        const float n4 = fmaxf(sqrtf(saa), 1e-12f), n6 = fmaxf(sqrtf(scc), 1e-12f);
+        const float a2 = __fdiv_rn(saa, __fmul_rn(n4, n4)), c2 = __fdiv_rn(scc, __fmul_rn(n6, n6)), acn = __fdiv_rn(sac, __fmul_rn(n4, n6));
+        const float s2 = __fadd_rn(__fadd_rn(c2, -2.f * acn), a2);
+        reg_w[obj * (int64_t)E + e] = __fdiv_rn(1.f, sqrtf(fmaxf(s2, 1e-30f)));
+        return;
+    }
     float n4 = 0.f, n6 = 0.f;
 #pragma unroll 4
     for (int c = 0; c < CH; ++c) {
-        const float2 s4 = FINAL ? make_float2(0.f, 0.f) : stat_s[0][c], s6 = FINAL ? make_float2(0.f, 0.f) : stat_s[1][c];
+        const float2 s4 = stat_s[0][c], s6 = stat_s[1][c];
         const float x4 = feature(Y4, X4, s4, c);
         const float x6 = feature(Y6, X6, s6, c);
         n4 = fmaf(x4, x4, n4);
@@ -445,7 +483,7 @@ __global__ void __launch_bounds__(256) gmw_edge_weight_kernel(MlpArgs a, float* 
     float a2 = 0.f, c2 = 0.f, ac = 0.f;
 #pragma unroll 4
     for (int c = 0; c < CH; ++c) {
-        const float2 s4 = FINAL ? make_float2(0.f, 0.f) : stat_s[0][c], s6 = FINAL ? make_float2(0.f, 0.f) : stat_s[1][c];
+        const float2 s4 = stat_s[0][c], s6 = stat_s[1][c];
         const float x4 = feature(Y4, X4, s4, c);
         const float x6 = feature(Y6, X6, s6, c);
         const float av = __fdiv_rn(x4, n4), cv = __fdiv_rn(x6, n6);

@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(256) tb_feat_kernel(const float* __restrict__ 
 
     // accumulator mapping: 4 own edges x 8 channels
     const int to = (tid & 15) * 4, tc = (tid >> 4) * 8;
-    float acc[4][8];
-#pragma unroll
+    float acc[4][8];                                         // sum over all steps; each step's 64 terms are summed separately
+#pragma unroll                                               // first (two-level summation: W has both signs and the products cancel)
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
@@ -342,6 +342,11 @@ __global__ void __launch_bounds__(256) tb_feat_kernel(const float* __restrict__ 
             }
         }
         __syncthreads();
+        float blk[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) blk[a][b] = 0.f;
 #pragma unroll 8
         for (int kk = 0; kk < FT; ++kk) {
             const float4 wv = *reinterpret_cast<const float4*>(WsT + kk * FT_WS + to);
@@ -352,8 +357,12 @@ __global__ void __launch_bounds__(256) tb_feat_kernel(const float* __restrict__ 
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(wa[a], fb[b], acc[a][b]);
+                for (int b = 0; b < 8; ++b) blk[a][b] = fmaf(wa[a], fb[b], blk[a][b]);
         }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] += blk[a][b];
     }
     // rsW / csW of the tile's own edges (fixed order over the 4 segments)
     red_s[seg * FT + lo] = wsum;

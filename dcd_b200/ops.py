@@ -256,6 +256,53 @@ def compute_pairs_kpts_depth(pred_extra_kpts_2d, pred_bbox_points, pred_offset_3
     return (depth, loc) if return_locations else depth
 
 
+# first channel of each regression group in the head's channel table of the reference configuration
+# (DGDE/runs/DGDE.yaml:27-28: [4],[2],[20],[3],[3],[8,8],[1],[1],[146],[219]; layers/utils.py:22-38 Converter_key2channel)
+DGDE_CHANNELS = {"3d_offset": 4, "extra_kpts_2d": 50, "extra_kpts_3d": 196}
+
+
+def frame_depths_from_map(pred_regression, indexs, pred_rots, P, pad_size, dims=None, batch_idxs=None, n: int = 73,
+                          channels=None, return_keypoints: bool = False):
+    """POI gather + image keypoints + edge solve + mean + 3D location in ONE launch, reading the regression map itself
+    (detector_infer.py:107 select_point_of_interest, :133 / :216-219 channel slices, :215-227 compute_pairs_kpts_depth,
+    :186-188 decode_location_flatten): pred_regression [B,C,H,W], indexs [N] int64 heat-map positions y * W + x of the kept
+    detections (select_topk), pred_rots [N] decoded yaw, P the 3x4 calibration ([3,4], per image [B,3,4] with batch_idxs, or
+    per object), pad_size [2] / [B,2], dims [N,3] or None -> (depth [N], locations [N,3]) and, with return_keypoints, the
+    image-space 2D keypoints [N,n,2] and template points [N,n,3] that generate_infer_data dumps (:228-236).  Inference-only."""
+    require_cuda(pred_regression, indexs, pred_rots)
+    _inference_only("frame_depths_from_map", pred_regression, pred_rots, dims)
+    fm = f32c(pred_regression)
+    B, C, H, W = fm.shape
+    ch = dict(DGDE_CHANNELS)
+    if channels:
+        ch.update(channels)
+    idx = indexs.reshape(-1).long().contiguous()
+    N, dev = idx.shape[0], fm.device
+    rot = f32c(pred_rots).reshape(-1)
+    if rot.shape[0] != N:
+        raise ValueError("pred_rots must hold one yaw per detection")
+    bi = batch_idxs.to(dev).to(torch.int32).contiguous() if batch_idxs is not None else None
+    if B > 1 and bi is None:
+        raise ValueError("batch_idxs is required for a multi-image map")
+    Pt = torch.as_tensor(P)
+    if Pt.dim() == 3 and Pt.shape[0] != N and batch_idxs is not None:
+        Pt = Pt.to(dev)[batch_idxs.to(dev).long()]
+    K = _calib_per_object(Pt, N, dev)
+    pad = _pad_per_object(pad_size, batch_idxs, N, dev)
+    d3 = f32c(dims) if dims is not None else None
+    depth = torch.empty((N,), dtype=torch.float32, device=dev)
+    loc = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    kimg = torch.empty((N, n, 2), dtype=torch.float32, device=dev) if return_keypoints else None
+    k3 = torch.empty((N, n, 3), dtype=torch.float32, device=dev) if return_keypoints else None
+    lo, hi = DGDE_CLAMP
+    if N:
+        check(_lib.lib().dcd_dgde_frame_fwd(ptr(fm), ptr(idx), ptr(bi), B, C, H, W, ch["extra_kpts_2d"], ch["extra_kpts_3d"],
+                                            ch["3d_offset"], ptr(rot), ptr(K), ptr(pad), ptr(d3), N, n, lo, hi,
+                                            FLAG_NORMALISE_2D | FLAG_SUB_B3, DOWN_RATIO, ptr(depth), ptr(loc), ptr(kimg), ptr(k3),
+                                            stream_ptr()), "dcd_dgde_frame_fwd")
+    return (depth, loc, kimg, k3) if return_keypoints else (depth, loc)
+
+
 def decode_location_flatten(points, offsets, depths, P, pad_size, batch_idxs=None):
     """Anno_Encoder.decode_location_flatten (DGDE/model/anno_encoder.py:147-161) with the calibration given as the
     3x4 matrix of the image ([3,4]) or per object ([N,3,4]) instead of Calibration objects -> locations [N,3].

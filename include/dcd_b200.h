@@ -94,6 +94,21 @@ int dcd_dgde_locate_fwd(const float* kpts_off, const float* kps3d, const float* 
                         const float* depth_in, int64_t N, int n, float lo, float hi, int flags, float down_ratio,
                         float* depth_out, float* locations, void* stream);
 
+/* The frame epilogue straight from the detector's regression map (row N2 fused into the load stage): ONE launch for
+ *   select_point_of_interest                                        DGDE/model/layers/utils.py:120-145, detector_infer.py:107
+ *   the key2channel slices '3d_offset', 'extra_kpts_2d', 'extra_kpts_3d'   detector_infer.py:133,216,219 (layers/utils.py:22-38)
+ *   image keypoints -> edge solve -> mean -> location (+ h/2)          as dcd_dgde_locate_fwd
+ * feature_maps [B,C,H,W]; index [N] int64 = y * W + x of each kept detection (select_topk's indices after the score
+ * threshold), batch_idx [N] int32 (NULL when B == 1); ch_*: first channel of each group in the head's channel table
+ * (DGDE.yaml: 4, 50, 196 for '3d_offset', 'extra_kpts_2d', 'extra_kpts_3d'); points = (index % W, index / W) as in
+ * select_topk (layers/utils.py:61-93).  rot [N] (decoded yaw), K [N,3,4], pad [N,2], dims [N,3] or NULL.
+ * Outputs (NULL to skip): depth_out [N], locations [N,3], kpts_img_out [N,n,2] / kps3d_out [N,n,3] (what
+ * generate_infer_data dumps for GMW, detector_infer.py:228-236).  A position outside the map yields NaN, never a fault. */
+int dcd_dgde_frame_fwd(const float* feature_maps, const int64_t* index, const int32_t* batch_idx, int64_t B, int C, int H, int W,
+                       int ch_kpts2d, int ch_kpts3d, int ch_offset3d, const float* rot, const float* K, const float* pad,
+                       const float* dims, int64_t N, int n, float lo, float hi, int flags, float down_ratio, float* depth_out,
+                       float* locations, float* kpts_img_out, float* kps3d_out, void* stream);
+
 /* Depth ensemble of the detector head (rest of row N4).  kp10 [N,10,2]: the regressed box keypoints (8 corners, bottom
  * centre, top centre; feature-map units), dims [N,3] (l,h,w), K [N,3,4] (f_u = K[0][0]).
  *   keypoint depths [N,3] = clamp(f_u * h / (relu(height) * down_ratio + eps), lo, hi) for the centre line and the two

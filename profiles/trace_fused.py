@@ -3,9 +3,8 @@
 
 Build the library with the trace hooks, run this on a GPU, then rebuild without them:
 
-    DCD_B200_NVCC_EXTRA=-DDCD_FUSED_TRACE python -m dcd_b200.build --force
-    gpurun -- 'python profiles/trace_fused.py > gpurun_out/trace.txt'
-    python -m dcd_b200.build --force
+    python -m dcd_b200.build --trace            # -> dcd_b200/libdcd_b200_trace.so, the product library is untouched
+    gpurun -- 'DCD_B200_LIB=$PWD/dcd_b200/libdcd_b200_trace.so python profiles/trace_fused.py > gpurun_out/trace.txt'
 
 Prints "slot tag delta_cycles" (slot 0 = converter warp 0, slot 1 = MMA warp of CTA 0).  Converter tags:
 1000*kind + {100 step start, 200 operand buffer free, 300 accumulators loaded, 400 operand stored, 500 arrived}
@@ -22,7 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dcd_b200  # noqa: E402
 from dcd_b200 import _lib, synth  # noqa: E402
 
-ob = synth.make_objects(N=8, n=73, seed=5)
+ob = synth.make_objects(N=int(os.environ.get('TRACE_OBJECTS', '8')), n=73, seed=5)
 model = dcd_b200.GMW(depth=12).cuda().load_reference_state_dict(synth.random_state_dict(7))
 with torch.no_grad():
     model(ob.kps_norm.cuda(), ob.kps_3d.cuda())

@@ -134,3 +134,59 @@ def test_poi_gather_vs_reference_fixture(golden):
         dcd_b200.select_point_of_interest(2, bi + 96 * 320, big, validate=True)
     assert bool(torch.isnan(dcd_b200.select_point_of_interest(2, bi + 96 * 320, big)).all())     # no fault without it
     assert dcd_b200.select_point_of_interest(2, bi[:, :0], big).shape == (2, 0, 440)
+
+
+def test_frame_from_regression_map_matches_gather_then_epilogue():
+    """Row N2 fused into the load stage: reading the [B,C,H,W] map directly == select_point_of_interest + channel slices +
+    the frame epilogue (bit-identical: same arithmetic on the same values), and the oracle's frame_locations."""
+    B, C, H, W, n = 2, 415, 96, 320, 73                      # DGDE.yaml: 415 regression channels, 384 x 1280 input / 4
+    g = torch.Generator().manual_seed(9)
+    ob = synth.make_objects(n=n, seed=81, counts=torch.tensor([37, 50]))
+    N = ob.N
+    fmap = torch.randn(B, C, H, W, generator=g) * 0.1
+    pos = torch.stack([torch.randperm(H * W, generator=g)[:N]])[0]
+    bi = ob.frame_id.clone()
+    pad_b = torch.tensor([[19.0, 5.0], [3.0, 7.0]])
+    pad = pad_b[bi]
+    px, py = (pos % W).float(), (pos // W).float()
+    ofs = torch.rand(N, 2, generator=g) - 0.5
+    # plant geometry-consistent values in the map: offsets such that (off + point + sub-pixel) * 4 - pad reproduces ob.kps
+    centre = torch.stack((px, py), dim=1) + ofs
+    off = (ob.kps + pad.unsqueeze(1)) / 4 - centre.unsqueeze(1)
+    ch = dcd_b200.ops.DGDE_CHANNELS
+    for d in range(N):
+        b, p = int(bi[d]), int(pos[d])
+        fmap[b, ch["3d_offset"]:ch["3d_offset"] + 2].view(2, -1)[:, p] = ofs[d]
+        fmap[b, ch["extra_kpts_2d"]:ch["extra_kpts_2d"] + 2 * n].view(2 * n, -1)[:, p] = off[d].reshape(-1)
+        fmap[b, ch["extra_kpts_3d"]:ch["extra_kpts_3d"] + 3 * n].view(3 * n, -1)[:, p] = ob.kps_3d[d].reshape(-1)
+    dims = torch.stack((torch.full((N,), 3.9), -ob.kps_3d[:, -1, 1], torch.full((N,), 1.6)), dim=1)
+    P = np.stack([np.array(synth.P2, dtype=np.float64)] * B)
+    fm, posd, rot, dimsd = cu(fmap, pos, ob.rot_y, dims)
+    with torch.no_grad():
+        depth, loc, kimg, k3o = dcd_b200.frame_depths_from_map(fm, posd, rot, P, pad_b.to(DEV), dims=dimsd, batch_idxs=bi.to(DEV),
+                                                               return_keypoints=True)
+        # un-fused route through the gather (one image at a time, like the reference's batch-1 inference loop)
+        for b in range(B):
+            sel = (bi == b).nonzero().reshape(-1).to(DEV)
+            pois = dcd_b200.select_point_of_interest(1, posd[sel].reshape(1, -1), fm[b:b + 1]).reshape(-1, C)
+            o2 = pois[:, ch["extra_kpts_2d"]:ch["extra_kpts_2d"] + 2 * n].reshape(-1, n, 2)
+            o3 = pois[:, ch["extra_kpts_3d"]:ch["extra_kpts_3d"] + 3 * n].reshape(-1, n, 3)
+            of = pois[:, ch["3d_offset"]:ch["3d_offset"] + 2]
+            pts = torch.stack((px, py), dim=1).to(DEV)[sel]
+            d2, l2 = dcd_b200.compute_pairs_kpts_depth(o2, pts, of, pad_b[b].to(DEV), o3, rot[sel], P[b], dims=dimsd[sel],
+                                                       return_locations=True)
+            assert torch.equal(depth[sel], d2) and torch.equal(loc[sel], l2)
+            assert torch.equal(k3o[sel], o3)
+    assert float((kimg.cpu() - ob.kps).abs().max()) < 2e-3
+    for b in range(B):
+        sel = (bi == b).nonzero().reshape(-1)
+        d_o, loc_o = O.frame_locations(off[sel], torch.stack((px, py), dim=1)[sel], ofs[sel], pad_b[b:b + 1], ob.kps_3d[sel],
+                                       ob.rot_y[sel], P[b], dims[sel])
+        assert rel_err(depth.cpu()[sel], d_o) < 1e-5
+        assert bool(((loc.cpu()[sel] - loc_o).abs() <= 1e-4 + 1e-5 * loc_o.abs()).all())
+    # a position outside the map: NaN, no fault
+    bad = posd.clone()
+    bad[0] = H * W + 5
+    with torch.no_grad():
+        d_bad, _ = dcd_b200.frame_depths_from_map(fm, bad, rot, P, pad_b.to(DEV), batch_idxs=bi.to(DEV))
+    assert bool(torch.isnan(d_bad[0])) and torch.equal(d_bad[1:], depth[1:])

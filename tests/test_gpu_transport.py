@@ -77,7 +77,7 @@ def test_transport_backward_small_vs_reference(golden, name, tol):
         assert e_o <= tol                                   # and an absolute bar against the FP64 evaluation
 
 
-@pytest.mark.parametrize("name,E,N,sharp,tol", [("transport_bwd_E2628_N2", 2628, 2, 0.0, 5e-4),
+@pytest.mark.parametrize("name,E,N,sharp,tol", [("transport_bwd_E2628_N2", 2628, 2, 0.0, 2e-3),
                                                 ("transport_bwd_E2628_sharp", 2628, 1, 0.03, 5e-2)])
 def test_transport_backward_full_size_vs_reference(golden, name, E, N, sharp, tol):
     """n = 73 (E = 2628): inputs regenerated from the fixture's seed, gradients compared on the stored 1/16 sample."""
