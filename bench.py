@@ -761,6 +761,25 @@ def run_sweep1m(args):
         if rank == 0:
             sys.stderr.write("CUDA-graph capture of solve + all-gather failed: %r\n" % (e,))
         torch.cuda.synchronize()
+    # two half-shards: the all-gather of the first half runs on NCCL's stream while the second half is being solved
+    ms_dgde_overlap = None
+    if world > 1:
+        h = (N + 1) // 2
+        mh = (m + 1) // 2
+        send2 = torch.zeros((2, mh), dtype=torch.float32, device=dev)
+        recv2 = torch.empty((2, world * mh), dtype=torch.float32, device=dev)
+        halves = [(0, h), (h, N)]
+
+        def dgde_step_overlap():
+            works = []
+            for i, (a0, a1) in enumerate(halves):
+                if a1 > a0:
+                    check(L.dcd_edge_solve_fwd(ptr(d_kps[a0:]), ptr(d_k3[a0:]), ptr(d_rot[a0:]), ptr(d_K[a0:]), a1 - a0, N_KPTS, 2.0, 80.0, 3,
+                                               0, ptr(send2[i]), stream_ptr()), "solve")
+                works.append(ctx.dist.all_gather_into_tensor(recv2[i], send2[i], async_op=True))
+            for w in works:
+                w.wait()
+        ms_dgde_overlap = timed(dgde_step_overlap, dg_steps, 5)
     ms_solve_only = time_kernel(lambda: check(L.dcd_edge_solve_fwd(ptr(d_kps), ptr(d_k3), ptr(d_rot), ptr(d_K), N, N_KPTS, 2.0, 80.0, 3,
                                                                    0, ptr(send), stream_ptr()), "solve"), reps=20)
     dgde_full = (recv.view(world, m)[:, :] if equal else None)
@@ -828,11 +847,13 @@ def run_sweep1m(args):
     ms, e2e_ms, mlp_ms_max, ms_dgde, ms_solve_only = ctx.max_over_ranks([ms, e2e_ms, mlp_ms, ms_dgde, ms_solve_only])
     if ms_dgde_graph is not None:
         ms_dgde_graph = ctx.max_over_ranks([ms_dgde_graph])[0]
+    if ms_dgde_overlap is not None:
+        ms_dgde_overlap = ctx.max_over_ranks([ms_dgde_overlap])[0]
     if rank == 0:
         fp32_peak = ctx.fp32_peak(clocks)
         value = N_total * args.steps / (ms * 1e-3)
         mlp_tflops = F_MLP * mlp_objs / (mlp_ms * 1e-3) / 1e12
-        best_dgde = min(ms_dgde, ms_dgde_graph) if ms_dgde_graph is not None else ms_dgde
+        best_dgde = min(x for x in (ms_dgde, ms_dgde_graph, ms_dgde_overlap) if x is not None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -853,7 +874,8 @@ def run_sweep1m(args):
                 "dgde_pipeline": {"what": "pipeline (i): DGDE inference edge solve + mean (a1 + a3) on the same %d objects, then ONE all-gather "
                                           "of the [N] depths; strong scaling" % N_total,
                                   "objects_per_s": N_total / (best_dgde * 1e-3), "ms_per_step": best_dgde,
-                                  "ms_eager": ms_dgde, "ms_cuda_graph": ms_dgde_graph, "ms_solve_kernel_only": ms_solve_only,
+                                  "ms_eager": ms_dgde, "ms_cuda_graph": ms_dgde_graph, "ms_two_chunks_overlapped": ms_dgde_overlap,
+                                  "ms_solve_kernel_only": ms_solve_only,
                                   "fp32_tflops_per_gpu": F_SOLVE * N / (ms_solve_only * 1e-3) / 1e12,
                                   "frac_fp32_roofline_kernel": F_SOLVE * N / (ms_solve_only * 1e-3) / 1e12 / fp32_peak,
                                   "allgather_and_launch_ms": best_dgde - ms_solve_only,

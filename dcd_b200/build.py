@@ -60,7 +60,9 @@ def build_library(force: bool = False, verbose: bool = False, out: str = LIB, ex
 
 
 if __name__ == "__main__":
-    if "--trace" in sys.argv:       # debug variant with the in-kernel timeline of the fused forward (profiles/trace_fused.py)
+    if "--scalar" in sys.argv:      # A/B variant: scalar instead of packed FP32 in the edge solve (profiles/ab_edge.py)
+        print(build_library(force=True, out=os.path.join(HERE, "libdcd_b200_scalar.so"), extra=["-DDCD_SCALAR_FP32"]))
+    elif "--trace" in sys.argv:       # debug variant with the in-kernel timeline of the fused forward (profiles/trace_fused.py)
         print(build_library(force=True, out=os.path.join(HERE, "libdcd_b200_trace.so"), extra=["-DDCD_FUSED_TRACE"]))
     else:
         print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -12,6 +12,7 @@
 //   * latency regime (a frame's worth of objects): ONE CTA PER OBJECT, every thread owns a fixed set of
 //     edges whose (i,j) offsets live in registers (n = 73), double-buffered staging with one
 //     __syncthreads per object, fixed-order cross-warp sum (deterministic).
+#include <cstdlib>
 #include "dcd_common.cuh"
 
 namespace dcd {
@@ -409,8 +410,17 @@ struct BlkGeom {
     static constexpr int OS = 4 * S4 + ((LPO - 4 * S4) % 32 + 32) % 32;               // object stride == LPO (mod 32) (114)
     static constexpr int NDUP = 4 * (LPO - 1) + NPART - NK + 1;                       // keypoints repeated after the n-th (35)
 };
+// per warp: terms v, Y, vC [G][OS] | per-lane sums | 5 per-object scalars | raw inputs of the NEXT group (v pixel row, X Y Z)
 template <int NK, int G>
-__host__ __device__ constexpr int blk_warp_floats() { return 3 * G * BlkGeom<NK>::OS + ((G * BlkGeom<NK>::LPO + 31) & ~31) + 8 * G; }
+__host__ __device__ constexpr int blk_warp_floats() {
+    return 3 * G * BlkGeom<NK>::OS + ((G * BlkGeom<NK>::LPO + 31) & ~31) + 8 * G + 4 * G * NK;
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 template <int NK, int G, bool FAST>
 __global__ void __launch_bounds__(GRP_WARPS * 32)
@@ -427,11 +437,26 @@ edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ 
     float* c_s = Y_s + G * OS;
     float* part_s = c_s + G * OS;                            // [G * LPO] per-lane sums
     float* sc_s = part_s + ((G * LPO + 31) & ~31);           // [5][G]: sin, cos, cy, fy, b3
+    float* rawv_s = sc_s + 8 * G;                            // [G * NK] pixel row of every keypoint of the next group
+    float* raw3_s = rawv_s + G * NK;                         // [G * NK * 3] its template points
     const bool normalise = (flags & DCD_NORMALISE_2D) != 0;
     const int64_t ngroups = (N + G - 1) / G;
+    const int64_t gstride = (int64_t)gridDim.x * GRP_WARPS;
     auto pos = [](int e) { return (e & 3) * S4 + (e >> 2); };   // interleaved position of element e inside an object
+    // asynchronous copy of a group's raw inputs (LDGSTS, 4 bytes per lane and instruction, fully coalesced): issued one group
+    // ahead, so the DRAM latency is covered by the previous group's edge loop instead of stalling the warp
+    auto prefetch = [&](int64_t g0) {
+        if (g0 >= ngroups) return;
+        const int64_t o0 = g0 * G;
+        const int cnt = (int)((N - o0 < G) ? N - o0 : G) * NK;
+        const float* kv = kps + o0 * NK * 2 + 1;
+        const float* k3 = kps3d + o0 * NK * 3;
+        for (int s = lane; s < cnt; s += 32) cp_async4(rawv_s + s, kv + 2 * s);
+        for (int s = lane; s < 3 * cnt; s += 32) cp_async4(raw3_s + s, k3 + s);
+    };
+    prefetch((int64_t)blockIdx.x * GRP_WARPS + warp);
 
-    for (int64_t grp = (int64_t)blockIdx.x * GRP_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * GRP_WARPS) {
+    for (int64_t grp = (int64_t)blockIdx.x * GRP_WARPS + warp; grp < ngroups; grp += gstride) {
         const int64_t obj0 = grp * G;
         const int gcount = (int)((N - obj0 < G) ? N - obj0 : G);
         if (lane < gcount) {
@@ -450,17 +475,17 @@ edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ 
             sc_s[4 * G + lane] = b3;
         }
         __syncwarp();
-        // ---- stage the group's keypoint terms (global keypoint index = obj0 * NK + slot: coalesced)
+        cp_async_commit_wait_all();                          // this group's raw inputs have landed
+        __syncwarp();
+        // ---- keypoint terms of the group from the raw staging buffer
         bool bad = false;
         const int slots = gcount * NK;
-        const float* kv = kps + obj0 * NK * 2 + 1;
-        const float* k3 = kps3d + obj0 * NK * 3;
 #pragma unroll 4
         for (int s0 = 0; s0 < slots; s0 += 32) {
             const int s = s0 + lane;
             if (s < slots) {
                 const int g = s / NK, i = s - g * NK;
-                const float4 t = keypoint_terms(__ldg(kv + 2 * s), __ldg(k3 + 3 * s), __ldg(k3 + 3 * s + 1), __ldg(k3 + 3 * s + 2),
+                const float4 t = keypoint_terms(rawv_s[s], raw3_s[3 * s], raw3_s[3 * s + 1], raw3_s[3 * s + 2],
                                                 sc_s[g], sc_s[G + g], normalise, sc_s[2 * G + g], sc_s[3 * G + g]);
                 const int p = g * OS + pos(i);
                 v_s[p] = t.x; Y_s[p] = t.y; c_s[p] = t.z;
@@ -473,6 +498,7 @@ edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ 
         }
         bad = __any_sync(0xffffffffu, bad);
         __syncwarp();
+        prefetch(grp + gstride);                             // the raw buffer is free again: fetch the next group behind the edge loop
         // ---- edges: lane = (object g, quad q), keypoints 4q .. 4q+3
         const int lanes = gcount * LPO;
         for (int L0 = 0; L0 < lanes; L0 += 32) {
@@ -492,9 +518,35 @@ edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ 
                 }
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
                 float accs = 0.f;
+                auto partner_pair = [&](int tp, float2& vj, float2& Yj, float2& cj) {      // partners tp, tp + 1 (tp + 1 <= NPART)
+                    const int o0 = (tp & 3) * S4 + (tp >> 2), o1 = ((tp + 1) & 3) * S4 + ((tp + 1) >> 2);
+                    vj = make_float2(pv[o0], pv[o1]); Yj = make_float2(pY[o0], pY[o1]); cj = make_float2(pc[o0], pc[o1]);
+                };
+                // partner pairs (tp, tp + 1) with tp = TP0, TP0 + 2, ..., TP1 pair with all four own keypoints: software-
+                // pipelined, the reciprocals of step k + 1 are issued before step k is refined and accumulated
+                constexpr int TP0 = 5, TP1 = (D - 1) | 1;                               // odd tp, tp >= 4 and tp + 1 <= D
+                {
+                    EdgeStage4 cur, nxt;
+                    float2 vj, Yj, cj;
+                    partner_pair(TP0, vj, Yj, cj);
+                    edge4_stage_a(ov, oY, oc, vj, Yj, cj, cur);
+#pragma unroll
+                    for (int tp = TP0; tp <= TP1; tp += 2) {
+                        if (tp + 2 <= TP1) {
+                            partner_pair(tp + 2, vj, Yj, cj);
+                            edge4_stage_a(ov, oY, oc, vj, Yj, cj, nxt);
+                        }
+                        float2 z[4];
+                        edge4_stage_b<FAST>(cur, lo, hi, z);
+                        acc0 = add2_rn(acc0, add2_rn(z[0], z[2]));
+                        acc1 = add2_rn(acc1, add2_rn(z[1], z[3]));
+                        if (tp + 2 <= TP1) cur = nxt;
+                    }
+                }
+                // the partial partner pairs at both ends of the window
 #pragma unroll
                 for (int tp = 1; tp <= NPART; tp += 2) {
-                    constexpr int dummy = 0; (void)dummy;
+                    if (tp >= TP0 && tp <= TP1) continue;
                     const bool has1 = tp + 1 <= NPART;
                     const int o0 = (tp & 3) * S4 + (tp >> 2), o1 = has1 ? ((tp + 1) & 3) * S4 + ((tp + 1) >> 2) : o0;
                     const float2 vj = make_float2(pv[o0], pv[o1]), Yj = make_float2(pY[o0], pY[o1]), cj = make_float2(pc[o0], pc[o1]);
@@ -790,21 +842,29 @@ int launch_edge_solve_fwd(const float* kps, const float* kps3d, const float* rot
                                                                                       depth_mean);                           \
     } while (0)
         if (n == 73) {
-            // n = 1 (mod 4): the register-blocked kernel, 7 objects (126 lanes) per warp group
-            constexpr int BG = 7;
-            const size_t bsmem = (size_t)GRP_WARPS * blk_warp_floats<73, BG>() * sizeof(float);
-            const int64_t bgroups = (N + BG - 1) / BG, bwant = (bgroups + GRP_WARPS - 1) / GRP_WARPS;
-            int bper = (int)((227 * 1024) / (bsmem + 1024));
-            if (bper > 8) bper = 8;
-            const int64_t bcap = (int64_t)sms * bper;
-            const int bgrid = (int)(bwant < bcap ? bwant : bcap);
-            if (fast) {
-                cudaFuncSetAttribute(edge_mean_block_kernel<73, BG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-                edge_mean_block_kernel<73, BG, true><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean);
-            } else {
-                cudaFuncSetAttribute(edge_mean_block_kernel<73, BG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-                edge_mean_block_kernel<73, BG, false><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean);
-            }
+            // n = 1 (mod 4): the register-blocked kernel; G objects (18 G lanes) per warp group.  More objects fill the last
+            // round's lanes better (G = 7: 126 of 128 lanes, G = 5: 90 of 96), fewer leave shared memory for more resident
+            // warps; measured on B200 (96 406 objects): G = 3 / 5 / 7 -> 0.179 / 0.164 / 0.167 ms.
+            int BG = 5;
+            if (const char* e = getenv("DCD_B200_BLOCK_G")) BG = atoi(e);      // tuning aid (profiles/): 3, 5 or 7
+#define DCD_LAUNCH_BLK(GV)                                                                                                  \
+    do {                                                                                                                    \
+        const size_t bsmem = (size_t)GRP_WARPS * blk_warp_floats<73, GV>() * sizeof(float);                                 \
+        const int64_t bgroups = (N + GV - 1) / GV, bwant = (bgroups + GRP_WARPS - 1) / GRP_WARPS;                           \
+        int bper = (int)((227 * 1024) / (bsmem + 1024));                                                                    \
+        if (bper > 8) bper = 8;                                                                                             \
+        const int64_t bcap = (int64_t)sms * bper;                                                                           \
+        const int bgrid = (int)(bwant < bcap ? bwant : bcap);                                                               \
+        if (fast) {                                                                                                         \
+            cudaFuncSetAttribute(edge_mean_block_kernel<73, GV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);  \
+            edge_mean_block_kernel<73, GV, true><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean); \
+        } else {                                                                                                            \
+            cudaFuncSetAttribute(edge_mean_block_kernel<73, GV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem); \
+            edge_mean_block_kernel<73, GV, false><<<bgrid, GRP_WARPS * 32, bsmem, st>>>(kps, kps3d, rot, K, N, lo, hi, flags, depth_mean); \
+        }                                                                                                                   \
+    } while (0)
+            if (BG == 3) DCD_LAUNCH_BLK(3); else if (BG == 5) DCD_LAUNCH_BLK(5); else DCD_LAUNCH_BLK(7);
+#undef DCD_LAUNCH_BLK
         } else if (false) {
             if (fast) DCD_LAUNCH_GRP(73, 7, true); else DCD_LAUNCH_GRP(73, 7, false);
         } else {

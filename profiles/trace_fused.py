@@ -30,9 +30,10 @@ L = ctypes.CDLL(_lib.LIB_PATH)
 buf = (ctypes.c_longlong * 8192)()
 n = (ctypes.c_int * 2)()
 L.dcd_debug_fused_trace(buf, n)
+t0 = min(buf[slot * 4096 + 1] for slot in range(2) if n[slot] > 0)
 for slot in range(2):
     prev = None
     for i in range(min(n[slot], 2048)):
         tag, t = buf[slot * 4096 + 2 * i], buf[slot * 4096 + 2 * i + 1]
-        print(slot, tag, t - (prev if prev is not None else t))
+        print(slot, tag, t - (prev if prev is not None else t), t - t0)       # slot, tag, cycles since the slot's previous event, absolute
         prev = t
