@@ -84,6 +84,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--objects", type=int, default=1 << 20, help="sweep1m: total objects")
     ap.add_argument("--quick", action="store_true", help="skip the per-stage breakdown (multi-rank scaling runs)")
+    ap.add_argument("--graph-collective", action="store_true", help="sweep1m: also time solve + all-gather replayed from a CUDA graph")
     return ap.parse_args()
 
 
@@ -256,7 +257,9 @@ class Ctx:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a short collective timeout: a rank that dies must not keep the others (and the box) waiting for 10 minutes
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=240))
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
         self.L = _lib.lib()
@@ -745,6 +748,8 @@ def run_sweep1m(args):
     # host round trips — SURVEY 7-H6: at 8 GPUs the solve is ~0.1 ms, comparable to the collective's launch latency)
     ms_dgde_graph = None
     try:
+        if world > 1 and not args.graph_collective:          # capturing an NCCL collective is opt-in: a failed capture on one
+            raise RuntimeError("skipped (pass --graph-collective)")   # rank would leave the others waiting in the collective
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -758,7 +763,7 @@ def run_sweep1m(args):
         ms_dgde_graph = timed(g.replay, dg_steps, 5)
     except Exception as e:                                   # graph capture of the collective unsupported here: report the eager figure only
         ms_dgde_graph = None
-        if rank == 0:
+        if rank == 0 and "skipped" not in str(e):
             sys.stderr.write("CUDA-graph capture of solve + all-gather failed: %r\n" % (e,))
         torch.cuda.synchronize()
     # two half-shards: the all-gather of the first half runs on NCCL's stream while the second half is being solved

@@ -19,7 +19,7 @@ def test_two_rank_nccl_run_matches_single_rank_bits(config, extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1", "--quick",
            "--no-cpu-baseline", "--config", config, "--chunk", "512"] + extra
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["value"] > 0
