@@ -266,6 +266,9 @@ edge_solve_fwd_warp_kernel(const float* __restrict__ kps, const float* __restric
 //   * objects with a non-finite term take a separate loop with torch's NaN-propagating clamps.
 // ---------------------------------------------------------------------------------------------
 constexpr int GRP_WARPS = 4;
+#ifndef BLK_PPS
+#define BLK_PPS 2          // partner pairs per software-pipeline step of the blocked kernel (8 interleaved chains)
+#endif
 __host__ __device__ constexpr int grp_stride(int n) { return n + 32 * ((n / 2 + 31) / 32); }   // == n (mod 32), >= n + n/2
 __host__ __device__ constexpr int grp_warp_floats(int n, int G) { return 3 * G * grp_stride(n) + ((G * n + 31) & ~31) + 8 * G; }   // v, Y, vC | per-slot sums | 5 per-object scalars
 
@@ -525,28 +528,36 @@ edge_mean_block_kernel(const float* __restrict__ kps, const float* __restrict__ 
                 // partner pairs (tp, tp + 1) with tp = TP0, TP0 + 2, ..., TP1 pair with all four own keypoints: software-
                 // pipelined, the reciprocals of step k + 1 are issued before step k is refined and accumulated
                 constexpr int TP0 = 5, TP1 = (D - 1) | 1;                               // odd tp, tp >= 4 and tp + 1 <= D
+                constexpr int PPS = BLK_PPS;                                              // partner pairs per pipeline step
+                constexpr int NSTEP = ((TP1 - TP0) / 2 + 1) / PPS;                      // full steps; leftover pairs go with the ends
+                constexpr int TPE = TP0 + 2 * PPS * NSTEP;                               // first tp not covered by the pipeline
                 {
-                    EdgeStage4 cur, nxt;
-                    float2 vj, Yj, cj;
-                    partner_pair(TP0, vj, Yj, cj);
-                    edge4_stage_a(ov, oY, oc, vj, Yj, cj, cur);
+                    EdgeStage<4 * PPS> cur, nxt;
+                    float2 vj[PPS], Yj[PPS], cj[PPS];
 #pragma unroll
-                    for (int tp = TP0; tp <= TP1; tp += 2) {
-                        if (tp + 2 <= TP1) {
-                            partner_pair(tp + 2, vj, Yj, cj);
-                            edge4_stage_a(ov, oY, oc, vj, Yj, cj, nxt);
+                    for (int p = 0; p < PPS; ++p) partner_pair(TP0 + 2 * p, vj[p], Yj[p], cj[p]);
+                    edge_stage_a<4 * PPS>(ov, oY, oc, vj, Yj, cj, cur);
+#pragma unroll
+                    for (int st = 0; st < NSTEP; ++st) {
+                        if (st + 1 < NSTEP) {
+#pragma unroll
+                            for (int p = 0; p < PPS; ++p) partner_pair(TP0 + 2 * PPS * (st + 1) + 2 * p, vj[p], Yj[p], cj[p]);
+                            edge_stage_a<4 * PPS>(ov, oY, oc, vj, Yj, cj, nxt);
                         }
-                        float2 z[4];
-                        edge4_stage_b<FAST>(cur, lo, hi, z);
-                        acc0 = add2_rn(acc0, add2_rn(z[0], z[2]));
-                        acc1 = add2_rn(acc1, add2_rn(z[1], z[3]));
-                        if (tp + 2 <= TP1) cur = nxt;
+                        float2 z[4 * PPS];
+                        edge_stage_b<FAST, 4 * PPS>(cur, lo, hi, z);
+#pragma unroll
+                        for (int w = 0; w < 4 * PPS; w += 2) {
+                            acc0 = add2_rn(acc0, z[w]);
+                            acc1 = add2_rn(acc1, z[w + 1]);
+                        }
+                        if (st + 1 < NSTEP) cur = nxt;
                     }
                 }
                 // the partial partner pairs at both ends of the window
 #pragma unroll
                 for (int tp = 1; tp <= NPART; tp += 2) {
-                    if (tp >= TP0 && tp <= TP1) continue;
+                    if (tp >= TP0 && tp < TPE) continue;
                     const bool has1 = tp + 1 <= NPART;
                     const int o0 = (tp & 3) * S4 + (tp >> 2), o1 = has1 ? ((tp + 1) & 3) * S4 + ((tp + 1) >> 2) : o0;
                     const float2 vj = make_float2(pv[o0], pv[o1]), Yj = make_float2(pY[o0], pY[o1]), cj = make_float2(pc[o0], pc[o1]);

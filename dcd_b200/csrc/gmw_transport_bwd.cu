@@ -12,7 +12,8 @@
 // is the same gradient (u4 = x, u3 as in the reference) with a single SPD solve.  S is (lambda/E)(I - Pn'^T Pn') for
 // the nearly doubly-stochastic Pn = E P: one eigenvalue ~1/E (the constant vector), the rest clustered — conjugate
 // gradients converge in 6-20 iterations (matrix-free: two passes over P per iteration, nothing E x E is formed) and in
-// FP32 are 100-1000x closer to the FP64 gradient than the reference's own FP32 Cholesky (oracle/README).
+// FP32 are 100-1000x closer to the FP64 gradient than the reference's own FP32 Cholesky (DESIGN.md section 2,
+// tests/test_gpu_transport.py).
 // Then, with M recovered from P = u K v, K = exp(-lambda M):  W = (dL/dM) / M  and
 //     dL/da_i = (sum_j W_ij) a_i - sum_j W_ij c_j,      dL/dc_j = (sum_i W_ij) c_j - sum_i W_ij a_i
 // (a, c the normalised features) as two tiled FP32 products that never materialise W.

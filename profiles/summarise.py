@@ -3,6 +3,7 @@
 
     python profiles/summarise.py launches gpurun_out/launches_r01.csv  profiles/r01_launches.md
     python profiles/summarise.py kernel   gpurun_out/prof_x.ncu-rep    profiles/r01_x.md [kernel-regex]
+    python profiles/summarise.py traffic  gpurun_out/prof_x.ncu-rep    <key> <kernel-substring>   # -> profiles/traffic.json
 
 `launches` aggregates the `--metrics gpu__time_duration.sum` launch list per kernel (count, total, share);
 `kernel` extracts the roofline-relevant raw metrics of every captured launch plus the hottest SASS
@@ -115,8 +116,37 @@ def kernel(rep, dst, regex=None):
                 f.write("| %d | %d | %.1f%% | %d | `%s` |\n" % (i, data[i][1], 100 * data[i][1] / tot, data[i][2], data[i][0][:90]))
 
 
+def traffic(rep, key, needle):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first captured launch whose name contains `needle`, stored under
+    `key` in profiles/traffic.json (what bench.py reports as roofline.traffic)."""
+    import json
+    import os
+    rows = ncu_csv(rep, "raw")
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = None
+    for r in rows[2:]:
+        if len(r) < len(hdr) or needle not in r[hdr.index("Kernel Name")]:
+            continue
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        break
+    if tot is None:
+        raise SystemExit("no launch of %r in %s" % (needle, rep))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[key] = tot
+    data.setdefault("_source", {})[key] = os.path.basename(rep)
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    print(key, tot)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
