@@ -267,7 +267,7 @@ edge_solve_fwd_warp_kernel(const float* __restrict__ kps, const float* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int GRP_WARPS = 4;
 #ifndef BLK_PPS
-#define BLK_PPS 2          // partner pairs per software-pipeline step of the blocked kernel (8 interleaved chains)
+#define BLK_PPS 4          // partner pairs per software-pipeline step of the blocked kernel (16 interleaved chains; 1 / 2 / 4 -> 0.164 / 0.165 / 0.157 ms)
 #endif
 __host__ __device__ constexpr int grp_stride(int n) { return n + 32 * ((n / 2 + 31) / 32); }   // == n (mod 32), >= n + n/2
 __host__ __device__ constexpr int grp_warp_floats(int n, int G) { return 3 * G * grp_stride(n) + ((G * n + 31) & ~31) + 8 * G; }   // v, Y, vC | per-slot sums | 5 per-object scalars
