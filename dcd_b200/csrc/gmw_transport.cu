@@ -6,13 +6,14 @@
 //   v = c / (K^T u);  P = (u * K) * v^T          with r = 1/E, c = 1/E                  model.py:186-191
 // Both training and validation loops consume P only through correspondenceLoss(P, eye) = sum(P) - 2 trace(P)
 // (GMW/main.py:456-457,526-527, lib/losses.py:22-26,115-119), so the kernels also return those two sums per object and
-// P itself is optional.  The backward (implicit differentiation with an E x E Cholesky, optimal_transport.py:75-128) is
-// not built.
+// P itself is optional.  The backward lives in gmw_transport_bwd.cu.
 //
-// K is E x E FP32 (27.6 MB per object at n = 73) in the caller's workspace; every Sinkhorn iteration streams it twice
+// K is built on the tensor cores (transport_k_tc_kernel) and kept as E x E FP32 (27.6 MB per object at n = 73) in the caller's
+// workspace; every Sinkhorn iteration streams it twice
 // (column pass K^T u with the rows split over 16 partial sums, row pass K w with a warp per row), deterministic: no
 // atomics on floating-point data.  The convergence test is a device flag, later iterations become no-ops.
-#include "gmw_mlp.cuh"
+#include <cstdlib>
+#include "gmw_tc_common.cuh"
 
 namespace dcd {
 namespace {
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(256) transport_norm_kernel(const float* __rest
     o[e] = n4; o[E + e] = n6; o[2 * (int64_t)E + e] = a2; o[3 * (int64_t)E + e] = c2;
 }
 
-// K tile: 64 x 64 outputs, 128-deep dot products of the normalised features, 4 x 4 outputs per thread
+// K tile on the CUDA cores (any E; the tensor-core kernel below needs E % 4 == 0): 64 x 64 outputs, 128-deep dot products of
+// the normalised features, 4 x 4 outputs per thread
 __global__ void __launch_bounds__(256) transport_k_kernel(const float* __restrict__ feat4, const float* __restrict__ feat6,
                                                           const float* __restrict__ nrm, int E, float lambda, float max_distance,
                                                           float* __restrict__ Kmat) {
@@ -89,6 +91,138 @@ __global__ void __launch_bounds__(256) transport_k_kernel(const float* __restric
             Kmat[(obj * E + i) * (int64_t)E + j] = expf(-lambda * fminf(m, max_distance));
         }
     }
+}
+
+// The same K tile on the tensor cores (tcgen05 + TMEM), 128 x 128 outputs per step: the 2628 x 2628 x 128 contraction of an
+// object (1.77 GFLOP) is the second dense contraction of GMW.  A CTA owns a 128-row block of net-4 edges: their L2-normalised
+// features are written once as FP16 hi/lo images in the MN-major 128B-swizzled UMMA layout (the layout of the MLP kernels'
+// activation operand: 8 consecutive edges of one channel are one 16-byte chunk, which is how the features lie in memory,
+// [128 channels][E]); it then walks the 128-column blocks of net-6 edges, building that operand the
+// same way, issuing D[i][j] = sum_c A[i][c] B[c][j] as 3 x 8 MMAs (FP16x3 split, both operands MN-major from shared memory,
+// FP32 accumulators in tensor memory) and turning the accumulators into K = exp(-lambda min(sqrt((c2 - 2 a.c) + a2), 5)) in
+// the epilogue (thread = row, all 8 warps).  Features are scaled by 2^8 before the split so that the low parts stay normal
+// FP16 numbers; the product carries 2^16, removed exactly.  Used when E is a multiple of 4 (16-byte row alignment).
+constexpr int KT = 128;                                 // tile edge
+constexpr size_t kKtcSmem = 4 * B_PART_BYTES + 2 * KT * sizeof(float) * 2 + 64;      // A hi/lo, B hi/lo, (a2, 1/n) x 2, barrier
+constexpr float kKtcScale = 256.f, kKtcUnscale = 1.f / 65536.f;
+constexpr uint32_t kIdescMnMn = kIdesc | (1u << 15);    // A MN-major as well (bit 15), B MN-major (bit 16), M = N = 128, F16 -> F32
+
+// one 128-edge block of one net -> FP16 hi/lo operand image; also the block's per-edge 1/norm and |normalised|^2
+__device__ __forceinline__ void ktc_build_operand(const float* __restrict__ feat, const float* __restrict__ nrm_n, const float* __restrict__ nrm_2,
+                                                  int E, int e0, unsigned char* hi, unsigned char* lo, float* sq_s, int tid) {
+    // 128 channels x 16 chunks of 8 edges = 2048 chunks, 256 threads: 8 chunks per thread; lanes run along the edge chunks
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+        const int id = it * 256 + tid;
+        const int c = id >> 4, eblk = id & 15;
+        const int e = e0 + eblk * 8;
+        float v[8];
+        const float* src = feat + (int64_t)c * E + e;
+        if (e + 8 <= E) {
+            const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+            const float4 n0 = *reinterpret_cast<const float4*>(nrm_n + e), n1 = *reinterpret_cast<const float4*>(nrm_n + e + 4);
+            v[0] = __fdiv_rn(x0.x, n0.x); v[1] = __fdiv_rn(x0.y, n0.y); v[2] = __fdiv_rn(x0.z, n0.z); v[3] = __fdiv_rn(x0.w, n0.w);
+            v[4] = __fdiv_rn(x1.x, n1.x); v[5] = __fdiv_rn(x1.y, n1.y); v[6] = __fdiv_rn(x1.z, n1.z); v[7] = __fdiv_rn(x1.w, n1.w);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (e + q < E) ? __fdiv_rn(src[q], nrm_n[e + q]) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] *= kKtcScale;
+        store_b8(hi, lo, c, eblk, v);
+    }
+    if (tid < KT) sq_s[tid] = (e0 + tid < E) ? nrm_2[e0 + tid] : 0.f;
+}
+
+__global__ void __launch_bounds__(256, 1) transport_k_tc_kernel(const float* __restrict__ feat4, const float* __restrict__ feat6,
+                                                                const float* __restrict__ nrm, int E, float lambda, float max_distance,
+                                                                float* __restrict__ Kmat) {
+    extern __shared__ __align__(1024) unsigned char ksm[];
+    unsigned char* A_hi = ksm;
+    unsigned char* A_lo = A_hi + B_PART_BYTES;
+    unsigned char* B_hi = A_lo + B_PART_BYTES;
+    unsigned char* B_lo = B_hi + B_PART_BYTES;
+    float* a2_s = reinterpret_cast<float*>(B_lo + B_PART_BYTES);       // [128] |a_i|^2 of the row block
+    float* c2_s = a2_s + KT;                                            // [128] |c_j|^2 of the current column block
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ksm + 4 * B_PART_BYTES + 2 * KT * sizeof(float) * 2);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int64_t obj = blockIdx.y;
+    const int i0 = blockIdx.x * KT;
+    const float* nr = nrm + obj * 4 * (int64_t)E;           // [4][E]: |f4|, |f6|, |a|^2, |c|^2 (transport_norm_kernel)
+    const float* f4 = feat4 + obj * (int64_t)CH * E;
+    const float* f6 = feat6 + obj * (int64_t)CH * E;
+    float* Kobj = Kmat + obj * (int64_t)E * E;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 128);
+    ktc_build_operand(f4, nr, nr + 2 * (int64_t)E, E, i0, A_hi, A_lo, a2_s, tid);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    const int quarter = warp & 3, half = warp >> 2;          // TMEM lane quarter (rows), column half
+    const int row = 32 * quarter + lane;                     // this thread's row of the tile
+    const int i = i0 + row;
+    const float a2 = a2_s[row];
+    uint32_t phase = 0;
+    for (int j0 = 0; j0 < E; j0 += KT) {
+        ktc_build_operand(f6, nr + (int64_t)E, nr + 3 * (int64_t)E, E, j0, B_hi, B_lo, c2_s, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
+            uint32_t acc = 0;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {          // Ah.Bl + Al.Bh + Ah.Bh
+                const uint32_t pa = smem_u32(term == 1 ? A_lo : A_hi);
+                const uint32_t pb = smem_u32(term == 0 ? B_lo : B_hi);
+#pragma unroll
+                for (int ks = 0; ks < CH / 16; ++ks) {
+                    umma_f16_ss(tmem_d, smem_desc(pa + ks * B_KSTEP, B_LBO, B_SBO), smem_desc(pb + ks * B_KSTEP, B_LBO, B_SBO), kIdescMnMn, acc);
+                    acc = 1;
+                }
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // epilogue: thread = row i, 64 columns of this warp's half
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            const int col0 = half * 64 + cc * 32;
+            tmem_ld32(tmem_d + ((uint32_t)(32 * quarter) << 16) + (uint32_t)col0, v);
+            if (i < E) {
+                float* dst = Kobj + (int64_t)i * E + j0 + col0;
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float dot = v[q + t] * kKtcUnscale;
+                        const float m = sqrtf(fmaxf(__fadd_rn(__fadd_rn(c2_s[col0 + q + t], -2.f * dot), a2), 1e-30f));
+                        o[t] = expf(-lambda * fminf(m, max_distance));
+                    }
+                    const int j = j0 + col0 + q;
+                    if (j + 4 <= E) *reinterpret_cast<float4*>(dst + q) = make_float4(o[0], o[1], o[2], o[3]);
+                    else
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (j + t < E) dst[q + t] = o[t];
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                     // accumulators read, B operand and c2_s free for the next block
+        tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tmem_d, 128);
 }
 
 // column pass: partial[obj][chunk][j] = sum over the chunk's rows i of K[i][j] * u[i]
@@ -244,9 +378,16 @@ int launch_gmw_transport_fwd(const float* feat4, const float* feat6, int64_t N, 
     const float rc = 1.0f / (float)E;                        // r = c = 1 / E (model.py:186-190)
     cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
     transport_norm_kernel<<<dim3(eb, (unsigned)N), 256, 0, st>>>(feat4, feat6, N, E, nrm);
-    constexpr int kSmem = 2 * CH * 64 * sizeof(float);
-    cudaFuncSetAttribute(transport_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    transport_k_kernel<<<dim3(tb, tb, (unsigned)N), 256, kSmem, st>>>(feat4, feat6, nrm, E, lambda, 5.0f, Kmat);
+    const char* ktc_env = getenv("DCD_B200_KTC");          // (being validated: opt-in for now)
+    if ((E & 3) == 0 && ktc_env != nullptr && ktc_env[0] == '1') {
+        // tensor-core tiles (rows of K 16-byte aligned)
+        cudaFuncSetAttribute(transport_k_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKtcSmem);
+        transport_k_tc_kernel<<<dim3((unsigned)((E + KT - 1) / KT), (unsigned)N), 256, kKtcSmem, st>>>(feat4, feat6, nrm, E, lambda, 5.0f, Kmat);
+    } else {
+        constexpr int kSmem = 2 * CH * 64 * sizeof(float);
+        cudaFuncSetAttribute(transport_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        transport_k_kernel<<<dim3(tb, tb, (unsigned)N), 256, kSmem, st>>>(feat4, feat6, nrm, E, lambda, 5.0f, Kmat);
+    }
     transport_fill_kernel<<<(unsigned)((N * e + 255) / 256), 256, 0, st>>>(u, (int64_t)(N * e), rc);
     DCD_CHECK_LAUNCH();
     // optimal_transport.py:63-69: the test at the top of iteration 0 compares u = r with u_prev = 1 (never close), so

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""profiles/r02_runs/*.json (bench.py lines of the multi-GPU runs) -> profiles/r02_scaling.md."""
+import glob
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(path):
+    lines = [l for l in open(path).read().strip().splitlines() if l.startswith("{")]
+    return json.loads(lines[-1])
+
+
+def main():
+    out = ["# Round-2 multi-GPU records (one 8xB200 node, NCCL over NVSwitch; `bench.py --config ... --gpus N`)", "",
+           "Every line is a `bench.py` JSON line kept verbatim under `profiles/r02_runs/`; times are CUDA events, max over ranks;",
+           "rank 0 recomputed rank 1's shard in each run and found the gathered depths bit-identical (`shard_check`).", ""]
+    rows = {}
+    for f in sorted(glob.glob(os.path.join(HERE, "r02_runs", "bench_*gpu.json"))):
+        name = os.path.basename(f)
+        cfg, n = name[len("bench_"):].rsplit("_", 1)
+        rows.setdefault(cfg, {})[int(n.replace("gpu.json", ""))] = load(f)
+    if "sweep1m" in rows:
+        r = rows["sweep1m"]
+        base = r.get(1)
+        out += ["## configs[3]: 2^20-object sweep, STRONG scaling, all-gather of the depths inside the timed region", "",
+                "Pipeline (ii), the metric: compute_z + edge-weight MLP + softmax-weighted depth.", "",
+                "| GPUs | objects/s | e2e objects/s | s per step | speed-up | bit-identical shard |", "|---:|---:|---:|---:|---:|---|"]
+        for n in sorted(r):
+            l = r[n]
+            sp = "%.2fx" % (l["value"] / base["value"]) if base else "-"
+            out.append("| %d | %.0f | %.0f | %.3f | %s | %s |" % (n, l["value"], l["e2e"]["value"], l["ms_per_step"] / 1e3, sp,
+                                                                   (l.get("shard_check") or {}).get("bit_identical", "n/a")))
+        out += ["", "Pipeline (i): DGDE inference edge solve + mean (a1 + a3), then ONE all-gather of the [N] depths.", "",
+                "| GPUs | objects/s | ms per step | solve kernel only (ms) | all-gather + launch (ms) | two overlapped half-shards (ms) | CUDA graph (ms) | speed-up |",
+                "|---:|---:|---:|---:|---:|---:|---:|---:|"]
+        for n in sorted(r):
+            d = r[n]["stages"]["dgde_pipeline"]
+            sp = "%.2fx" % (d["objects_per_s"] / base["stages"]["dgde_pipeline"]["objects_per_s"]) if base else "-"
+            fmt = lambda v: "-" if v is None else "%.4f" % v   # noqa: E731
+            out.append("| %d | %.3g | %.4f | %.4f | %.4f | %s | %s | %s |" % (n, d["objects_per_s"], d["ms_per_step"], d["ms_solve_kernel_only"],
+                                                                              d["allgather_and_launch_ms"], fmt(d.get("ms_two_chunks_overlapped")),
+                                                                              fmt(d.get("ms_cuda_graph")), sp))
+        out += ["", "What limits pipeline (i): the solve shrinks with 1/N (0.22 ms for 131 072 objects at N = 8) while the all-gather of 4 MB",
+                "costs a constant ~35 us of launch + NVSwitch latency (SURVEY 7-H6): 14 % of the step at 8 GPUs.  Splitting the shard into",
+                "two halves to overlap the first half's collective with the second half's solve does not pay (a second collective latency",
+                "plus two smaller, less efficient launches); the GMW pipeline (ii) scales at 7.96x because its step is seconds long.", ""]
+    if "stress256" in rows:
+        r = rows["stress256"]
+        base = r.get(1)
+        out += ["## configs[4]: 256 keypoints / 32 640 edges, GMW training step (forward + backward) on 64 objects per GPU, weak scaling", "",
+                "| GPUs | objects/s | ms per step | fwd ms | bwd ms | forward HBM GB/s (frac of measured) | DGDE a1(train)+a9, 4096 objects/GPU (objects/s per GPU) |",
+                "|---:|---:|---:|---:|---:|---:|---:|"]
+        for n in sorted(r):
+            l = r[n]
+            ro = l["roofline"]
+            out.append("| %d | %.0f | %.1f | %.1f | %.1f | %.0f (%.2f) | %.3g |" % (n, l["value"], l["ms_per_step"], ro["forward_ms_per_step"],
+                                                                                 ro["backward_ms_per_step"], ro["achieved"], ro["frac"],
+                                                                                 l["stages"]["dgde_train_pattern_n256"]["objects_per_s"]))
+        out.append("")
+    open(os.path.join(HERE, "r02_scaling.md"), "w").write("\n".join(out))
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()
