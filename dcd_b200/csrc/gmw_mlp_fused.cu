@@ -26,10 +26,6 @@
 #include <type_traits>
 #include "gmw_tc_common.cuh"
 
-#ifndef DCD_FUSED_SLEEP_NS
-#define DCD_FUSED_SLEEP_NS 0        // back-off of the weight loaders' and statistics warps' barrier waits (0: spin)
-#endif
-
 namespace dcd {
 // Optional in-kernel timeline (build with -DDCD_FUSED_TRACE, see profiles/trace_fused.py): lane 0 of converter warp 0
 // and of the MMA warp of CTA 0 record (tag, clock64) pairs; read back with dcd_debug_fused_trace().
@@ -56,33 +52,39 @@ __device__ int g_trace_n[3];
 #define TR_DECL
 #define TR(slot, tag) do { } while (0)
 #endif
+#if defined(DCD_FUSED_TRACE) && DCD_FUSED_TRACE + 0 >= 2
+#define TRF(slot, tag) TR(slot, tag)     // fine-grained tags (they cost ~100 clk each: the coarse level keeps the timeline honest)
+#else
+#define TRF(slot, tag) do { } while (0)
+#endif
 namespace {
 
-constexpr int FCS = 16;             // CTAs per group = edge slices per object; a group works on TWO objects at a time
+constexpr int FCS = 24;             // CTAs per group = edge slices per object
+constexpr int FOBJ = 3;             // a group works on THREE objects at a time (same net, same layer weights)
 constexpr int FCONV_WARPS = 12;     // converter warps: 4 TMEM lane quarters x 3 units (16 edges) of a 48-edge sub-tile
 constexpr int FCONV_THREADS = 32 * FCONV_WARPS;
 constexpr int FTHREADS = FCONV_THREADS + 128;   // + 4 service warps: weight loads (all 4), MMA issue (the first)
 constexpr int FSUB = 48;            // edges per MMA sub-tile
-constexpr int FES_MAX = 168;        // edges per CTA and object
-constexpr uint32_t FT_SLOT = 192;   // tensor-memory columns: D of object half 0 = [0, 176), of half 1 = [192, 368),
-constexpr uint32_t FT_W = 384;      //                        weights hi = [384, 448), lo = [448, 512)
+constexpr int FES_MAX = 112;        // edges per CTA and object (FOBJ * FES_MAX = 336 = 7 sub-tiles)
+constexpr uint32_t FT_W = 384;      // tensor-memory columns: D = [0, 336) (three objects side by side), weights hi = [384, 448), lo = [448, 512)
 constexpr uint32_t FB_SBO = 128;    // B operand: bytes between 8-edge blocks of one 8-channel block
 constexpr uint32_t FB_LBO = 768;    //            bytes between 8-channel blocks (6 edge blocks)
 constexpr uint32_t FB_PART = 16 * FB_LBO;   // 12 KB: hi or lo part of one sub-tile
 
 constexpr size_t SMF_X = 0;
-constexpr size_t SMF_B = SMF_X + (size_t)2 * FES_MAX * CH * sizeof(float);      // [2 buffers]{hi, lo}
-constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [2][3][128] float2 (mean, M2) + count tables + [2][128] statistics
-constexpr size_t SMF_BAR = SMF_PART + (2 * 3 * CH + 32 + 2 * CH) * sizeof(float2);
+constexpr size_t SMF_B = SMF_X + (size_t)FOBJ * FES_MAX * CH * sizeof(float);   // [2 buffers]{hi, lo}
+constexpr size_t SMF_PART = SMF_B + 4 * FB_PART;                                // [3][3][128] float2 (mean, M2) / (mean, rstd) + count tables
+constexpr size_t SMF_BAR = SMF_PART + (FOBJ * 3 * CH + 64) * sizeof(float2);
 constexpr size_t kFusedSmem = SMF_BAR + 128;
 static_assert(kFusedSmem <= 232448, "shared memory budget");
-static_assert(2 * 6 * FES_MAX * sizeof(float) <= 4 * FB_PART, "edge features are staged in the operand buffers");
-static_assert(2 * FES_MAX <= FCONV_THREADS, "one converter thread per staged edge");
+static_assert(FOBJ * 6 * FES_MAX * sizeof(float) <= 4 * FB_PART, "edge features are staged in the operand buffers");
+static_assert(FOBJ * FES_MAX <= FCONV_THREADS, "one converter thread per staged edge");
 // mbarriers (8 bytes each, at SMF_BAR)
-enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_COUNT = 6 };
+enum { BAR_FULL0 = 0, BAR_FULL1 = 1, BAR_DONE0 = 2, BAR_DONE1 = 3, BAR_PDONE = 4, BAR_WREADY = 5, BAR_STAT0 = 6, BAR_COUNT = 9 };
 // hardware named barriers (a blocked warp takes no issue slots): 0 = CTA, 1 = converters, 2..4 = the units of the epilogue,
-// then the hand-offs between the converters (12 warps) and the statistics warps (3 warps): one side arrives, the other waits
-enum { NB_STAT0 = 5, NB_STAT1 = 6, NB_PART = 7 };
+// 5..7 = partial statistics of object 0..2 posted: the converters (12 warps) arrive, the statistics warps (3 warps) wait;
+// 8 = the statistics warps among themselves
+enum { NB_PART0 = 5, NB_STATW = 8 };
 constexpr int FSTAT_THREADS = 96;
 constexpr int NB_THREADS = FCONV_THREADS + FSTAT_THREADS;
 
@@ -107,16 +109,16 @@ __device__ __forceinline__ void ld_weights8(const uint32_t* p, uint32_t* r) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// wait of a warp that has nothing else to do for a whole layer (weight loaders): back off instead of spinning in the issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+// mbarrier wait that backs off between tests (ptxas drops try_wait's suspend-time hint on sm_100a: the default time-out is
+// short and a spinning warp takes issue slots from the warps it is waiting for)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
     uint32_t done;
-    do {
+    for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-#if DCD_FUSED_SLEEP_NS > 0
-        if (!done) __nanosleep(DCD_FUSED_SLEEP_NS);
-#endif
-    } while (!done);
+        if (done) break;
+        __nanosleep(ns);
+    }
 }
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -226,8 +228,9 @@ __device__ __forceinline__ void issue_sub_gemm(uint32_t tmem_d, uint32_t a_hi, u
 //     Wf = W1 . Wp,   bf = W1 . bp + b1        (FP64 accumulation, rounded once to FP32; tc_fold_prep_kernel)
 // which removes a third of the GEMM layers (24 instead of 36 per net; SURVEY 8d: report F_m with 24).
 // Per matrix m = (net, block, j) with j = 0: Wf, j = 1: W2 this kernel writes the power-of-two FP16 scale, the bias
-// and the pre-split weight image [row = out channel][128 x u32]: columns 0-63 the FP16 pairs (k = 2c, 2c+1) of
-// scale*W (hi part), columns 64-127 the lo parts — exactly the tensor-memory image of the A operand.
+// and the pre-split weight image: per row (= out channel) 128 x u32, columns 0-63 the FP16 pairs (k = 2c, 2c+1) of
+// scale*W (hi part), columns 64-127 the lo parts — the tensor-memory image of the A operand — stored as
+// [half][chunk of 8 columns][row][8] so that the 32 rows a warp loads lie next to each other.
 __global__ void __launch_bounds__(1024) fused_prep_kernel(const float* __restrict__ p4, const float* __restrict__ p6, int depth,
                                                          const float* __restrict__ fold, float2* __restrict__ scales2,
                                                          float* __restrict__ bias2, uint32_t* __restrict__ img) {
@@ -271,8 +274,9 @@ __global__ void __launch_bounds__(1024) fused_prep_kernel(const float* __restric
         const float w0 = wf_s[(2 * c) * CH + row] * scale, w1 = wf_s[(2 * c + 1) * CH + row] * scale;
         const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
         const __half l0 = __float2half_rn(w0 - __half2float(h0)), l1 = __float2half_rn(w1 - __half2float(h1));
-        out[row * CH + c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        out[row * CH + 64 + c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        // [half][chunk of 8 columns][row][8]: a warp (32 rows) fetches one chunk as 1 KB of consecutive bytes
+        out[(((c >> 3)) * CH + row) * 8 + (c & 7)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        out[((8 + (c >> 3)) * CH + row) * 8 + (c & 7)] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
 }
 
@@ -287,19 +291,19 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
     TR_DECL
     const int ch = 32 * quarter + lane;                      // this thread's channel = TMEM lane = weight row
-    const uint32_t rank = blockIdx.x % FCS, group = blockIdx.x / FCS;   // 16 consecutive CTAs form a group (co-resident: cooperative launch)
+    const uint32_t rank = blockIdx.x % FCS, group = blockIdx.x / FCS;   // 24 consecutive CTAs form a group (co-resident: cooperative launch)
     const int E = L.E, EP = L.EP, depth = L.depth;
-    const int ES = 8 * ((E + 127) / 128);                    // edges per CTA and object (16 * ES == EP)
-    const int xrows = ES >> 2;                               // float4 rows of the residual stream per object
-    const int nsub = (ES + FSUB - 1) / FSUB;
+    const int upo = (E + 16 * FCS - 1) / (16 * FCS);         // 16-edge units per object in this CTA
+    const int ES = 16 * upo;                                 // edges per CTA and object
+    const int ntile = upo;                                   // 48-column tiles of the CTA: FOBJ * ES == 48 * upo
     const int nphase = 2 * depth;                            // per block: folded preconv.conv1, conv2
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* Xs = reinterpret_cast<float4*>(smem + SMF_X);
     unsigned char* Bbuf = smem + SMF_B;
-    float2* part2_s = reinterpret_cast<float2*>(smem + SMF_PART);            // [2 (alternating)][3][128] (mean, M2) per unit stream
-    float2* tab_s = part2_s + 2 * 3 * CH;                                    // counts, see below
-    float2* stat_s = tab_s + 32;                                             // [2 object halves][128] (mean, rstd) of the latest context norm
+    float2* pbuf = reinterpret_cast<float2*>(smem + SMF_PART);               // [3 objects][3 unit streams][128]: (mean, M2) posted by the
+                                                                             // converters, overwritten with (mean, rstd) by the statistics warps
+    float2* tab_s = pbuf + FOBJ * 3 * CH;                                    // count tables, see below
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMF_BAR);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SMF_BAR + 8 * BAR_COUNT);
 
@@ -310,18 +314,34 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         mbar_init(bar + BAR_DONE1, 1);
         mbar_init(bar + BAR_PDONE, 1);
         mbar_init(bar + BAR_WREADY, 4);
+        for (int o = 0; o < FOBJ; ++o) mbar_init(bar + BAR_STAT0 + o, 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // statistics merge weights: tab_s[q] = (n_q, n_q / n_cta) for the 3 unit streams of this CTA (q = 0..2),
-    // tab_s[4 + r] = (n_r, n_r / E) for the 16 slices of an object
-    if (tid < 3) {
+    // Columns of the CTA: unit u (16 columns) = object u / upo, its edges [16 (u % upo), +16) of the slice; unit u is converted by
+    // the converter warps with warp / 4 == u % 3.  The partial statistics of an object are kept per "unit stream" k = (unit index
+    // inside the object) % 3 — one converter warp per lane quarter each — so that the merge order does not depend on which of
+    // the three places an object takes.  Statistics merge weights:
+    //   tab_s[3 o + k]      = (n_ok, n_ok / n_cta)  valid edges of object o in unit stream k (the same for every o)
+    //   tab_s[9 + 3 o + k]  = (1 / n_ok or 0, -)
+    //   tab_s[32 + r]       = (n_r, n_r / N_s)      valid edges of the slice of rank r; s = r / 8: the three rank subsets the
+    //   tab_s[56 + s]       = (N_s, N_s / E)        statistics warps merge first
+    if (tid < 9) {
+        const int o = tid / 3, k = tid % 3;
         const int vld = max(0, min(ES, E - (int)rank * ES));
         int nq = 0;
-        for (int col0 = 16 * tid; col0 < ES; col0 += FSUB) nq += max(0, min(16, vld - col0));
+        for (int u = o * upo; u < (o + 1) * upo; ++u)
+            if ((u - o * upo) % 3 == k) nq += max(0, min(16, vld - 16 * (u - o * upo)));
         tab_s[tid] = make_float2((float)nq, vld > 0 ? (float)nq / (float)vld : 0.f);
-    } else if (tid >= 4 && tid < 4 + FCS) {
-        const int nr = max(0, min(ES, E - (tid - 4) * ES));
-        tab_s[tid] = make_float2((float)nr, (float)nr / (float)E);
+        tab_s[9 + tid] = make_float2(nq > 0 ? 1.0f / (float)nq : 0.f, 0.f);
+    } else if (tid >= 32 && tid < 32 + FCS) {
+        const int r = tid - 32, sb = r / 8;
+        const int nr = max(0, min(ES, E - r * ES));
+        const int ns = max(0, min(E, (sb + 1) * 8 * ES) - min(E, sb * 8 * ES));
+        tab_s[tid] = make_float2((float)nr, ns > 0 ? (float)nr / (float)ns : 0.f);
+    } else if (tid >= 56 && tid < 59) {
+        const int sb = tid - 56;
+        const int ns = max(0, min(E, (sb + 1) * 8 * ES) - min(E, sb * 8 * ES));
+        tab_s[tid] = make_float2((float)ns, (float)ns / (float)E);
     }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     tc_fence_before();
@@ -329,29 +349,33 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    // Work list of a group: "duals" = (net, object pair 2p, 2p + 1) — the two objects share the layer weights and take turns
-    // layer by layer.  PAIRED (reg_w != nullptr): pairs group, group + G, ... with both nets of a pair back to back (net 0 then
-    // net 1), so that the second net's final pass finds the first net's features parked by the very same threads and emits
-    // the edge weights itself (see the epilogue).  Otherwise (features requested, or too few objects): duals 2 p + net dealt
-    // round-robin, final features to global memory.  An odd object count runs its last object in both halves (one output).
+    // Work list of a group: "rounds" = (net, object triple 3p, 3p + 1, 3p + 2) — the three objects share the layer weights and
+    // follow each other through every layer, so the statistics exchange of one object's layer (drain of its last MMAs, L2
+    // round trip between the 24 CTAs) is hidden behind the other two objects' tiles.  PAIRED (reg_w != nullptr): triples
+    // group, group + G, ... with both nets of a triple back to back (net 0 then net 1), so that the second net's final pass
+    // finds the first net's features parked by the very same threads and emits the edge weights itself (see the epilogue).
+    // Otherwise (features requested, or too few objects): rounds 2 p + net dealt round-robin, final features to global memory.
+    // A last, incomplete triple repeats its last object (one output).
     const int64_t ngroups = gridDim.x / FCS;
     const bool paired = reg_w != nullptr;
-    const int64_t npairs = (L.N + 1) >> 1;
-    const int64_t nlist = paired ? npairs : 2 * npairs;      // entries dealt round-robin: pairs (paired) or duals
+    const int64_t ntrip = (L.N + FOBJ - 1) / FOBJ;
+    const int64_t nlist = paired ? ntrip : 2 * ntrip;        // entries dealt round-robin: triples (paired) or rounds
     const int64_t nmine = nlist > (int64_t)group ? (nlist - 1 - group) / ngroups + 1 : 0;
-    const int64_t nd = paired ? 2 * nmine : nmine;           // duals of this group
-    auto dual_pair = [&](int64_t d) { return paired ? (int64_t)group + (d >> 1) * ngroups : ((int64_t)group + d * ngroups) >> 1; };
-    auto dual_net = [&](int64_t d) { return paired ? (int)(d & 1) : (int)(((int64_t)group + d * ngroups) & 1); };
+    const int64_t nd = paired ? 2 * nmine : nmine;           // rounds of this group
+    auto round_trip = [&](int64_t d) { return paired ? (int64_t)group + (d >> 1) * ngroups : ((int64_t)group + d * ngroups) >> 1; };
+    auto round_net = [&](int64_t d) { return paired ? (int)(d & 1) : (int)(((int64_t)group + d * ngroups) & 1); };
 
     if (warp >= FCONV_WARPS) {
         // =====================================================================================================
-        // service warps: stream the layers' weight images into tensor memory; the first one issues the MMAs
+        // service warps: stream the layers' weight images into tensor memory; the first one issues the MMAs,
+        // the other three run the context-norm statistics exchange
         // =====================================================================================================
         uint32_t wr[64];
-        auto w_src = [&](int mat) { return wimg + ((size_t)mat * CH + ch) * CH; };
-        auto w_load = [&](const uint32_t* src, int half) {
+        // weight image of a matrix: [half (hi, lo)][chunk of 8 columns][row][8 x u32] — a warp's load of one chunk is 1 KB contiguous
+        auto w_load = [&](int mat, int half) {
+            const uint32_t* src = wimg + (size_t)mat * CH * CH + ((size_t)(half * 8) * CH + ch) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ld_weights8(src + 64 * half + 8 * i, wr + 8 * i);
+            for (int i = 0; i < 8; ++i) ld_weights8(src + (size_t)i * CH * 8, wr + 8 * i);
         };
         auto w_store = [&](int half) {
             uint32_t t[32];
@@ -368,145 +392,187 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + BAR_WREADY);
         };
-        uint32_t g = 0;                                       // running sub-tile step: operand buffer = g & 1
+        uint32_t g = 0;                                       // running tile step: operand buffer = g & 1
         uint32_t fpar = 0, wpar = 0, ppar = 0;                // parities: full[2] (bits), wready, pdone
-        // ---- context-norm statistics (service warps 1..3; the MMA warp takes no part).  The converters post one (mean, M2) per
-        //      unit stream and channel when a layer output of an object half is complete (NB_PART).  A statistics thread owns a
-        //      channel (the first warp two): it merges the 3 unit streams, publishes the slice's (mean, M2) in global memory for
-        //      the 15 other CTAs of the group (flagged words, see st_flagged), collects theirs, merges in rank order and posts
-        //      (mean, rstd) of the layer in shared memory (NB_STAT0/1).  All counts are constants of the launch: no divisions.
-        //      The converters never wait for the exchange unless it is slower than the other half's layer.
-        const bool stat_warp = warp > FCONV_WARPS;
+        // ---- context-norm statistics (service warps 1..3; the MMA warp takes no part).  Every converter warp posts one (mean, M2)
+        //      per object and layer for its unit stream (NB_PART0 + object).  A statistics thread owns a channel (the first warp
+        //      two): it merges the 3 unit streams, publishes the slice's (mean, M2) in global memory for the 23 other CTAs of the
+        //      group (flagged words, see st_flagged), collects theirs, merges in rank order and hands (mean, rstd) of the layer
+        //      back through the converters' own partial slots (BAR_STAT0 + object).  All counts are constants of the launch: no
+        //      divisions.  The converters wait for an exchange only if it takes longer than the other two objects' tiles.
         const int nrep = warp == FCONV_WARPS + 1 ? 2 : 1;
         const float inv_em1 = 1.0f / (float)(E - 1);
-        uint32_t sxc0 = 0, sxc1 = 0;                          // exchanges done per object half: slot = count & 1, flag = (count >> 1) & 1
-        uint32_t ecount = 0;                                  // events handled (alternates the partials buffer)
-        auto stat_event = [&](int sig) {
-            TR(2, 700 + sig);
-            nbar_sync(NB_PART, NB_THREADS);
-            TR(2, 710 + sig);
-            const float2* pbuf = part2_s + (ecount & 1u) * 3 * CH;
-            const uint32_t xc = sig ? sxc1 : sxc0;
-            const uint32_t slot = xc & 1u, flag = (xc >> 1) & 1u;
-            float2* xrow0 = xg + ((size_t)((group * 2 + sig) * 2 + slot) * FCS) * CH;      // [rank][128] of this group, half and slot
+        uint32_t sxc = 0;                                     // exchanges done per object, mod 4 (2 bits each): slot = count & 1, flag = (count >> 1) & 1
+        auto ev_row = [&](int o) {
+            const uint32_t xc = (sxc >> (2 * o)) & 3u;
+            return xg + ((size_t)((group * FOBJ + o) * 2 + (xc & 1u)) * FCS) * CH;        // [rank][128] of this group, object and slot
+        };
+        auto ev_flag = [&](int o) { return (sxc >> (2 * o + 1)) & 1u; };
+        // the 12 partial posts of (object, layer) are in: merge the unit streams, publish the slice
+        auto ev_publish = [&](int o) {
+            TR(2, 700 + o);
+            nbar_sync(NB_PART0 + o, NB_THREADS);
+            TR(2, 710 + o);
+            float2* xrow0 = ev_row(o);
+            const uint32_t flag = ev_flag(o);
             for (int rep = 0; rep < nrep; ++rep) {
                 const int c = rep ? 96 + lane : 32 * (warp - FCONV_WARPS - 1) + lane;
                 float2 q[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) q[k] = pbuf[k * CH + c];
+                for (int k = 0; k < 3; ++k) q[k] = pbuf[(o * 3 + k) * CH + c];
                 float m = 0.f, M2 = 0.f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) m = fmaf(tab_s[k].y, q[k].x, m);
+                for (int k = 0; k < 3; ++k) m = fmaf(tab_s[o * 3 + k].y, q[k].x, m);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float dd = q[k].x - m;
-                    M2 += fmaf(tab_s[k].x * dd, dd, q[k].y);
+                    const float nk = tab_s[o * 3 + k].x, dd = q[k].x - m;
+                    if (nk > 0.f) M2 += fmaf(nk * dd, dd, q[k].y);
                 }
                 st_flagged(xrow0 + rank * CH + c, m, M2, flag);
             }
-            TR(2, 720 + sig);
-            for (int rep = 0; rep < nrep; ++rep) {
-                const int c = rep ? 96 + lane : 32 * (warp - FCONV_WARPS - 1) + lane;
-                const float2* xrow = xrow0 + c;
-                // all 16 slices (the own one included) in flight at once, re-read until every word carries this exchange's flag
-                float2 v[FCS];
-                for (;;) {
+            TR(2, 720 + o);
+        };
+        // Collect the 24 slices (the own one included) and hand (mean, rstd) to the converters.  Each statistics warp takes 8
+        // ranks for all 128 channels (a lane: 4 channels x 8 flagged words in flight at once, re-read until every word carries
+        // this exchange's flag) and merges them; the three subset results meet in the object's partial slots, then every channel
+        // is finished by one thread (rank subsets in order: the same operations in every CTA of the group).
+        auto ev_finish = [&](int o) {
+            const int sb = warp - FCONV_WARPS - 1;            // rank subset of this warp: ranks 8 sb .. 8 sb + 7
+            const float2* xrow0 = ev_row(o) + (size_t)(8 * sb) * CH + lane;
+            const uint32_t flag = ev_flag(o);
+            float2 v[4][8];
+            for (;;) {
 #pragma unroll
-                    for (int r = 0; r < FCS; ++r) v[r] = ld_volatile_f2(xrow + r * CH);
-                    uint32_t bad = 0;
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int r = 0; r < FCS; ++r) bad |= (__float_as_uint(v[r].y) >> 31) ^ flag;
-                    if (!bad) break;
-                    __nanosleep(100);                                             // (slices still missing: poll at a low rate)
+                    for (int r = 0; r < 8; ++r) v[q][r] = ld_volatile_f2(xrow0 + r * CH + 32 * q);
+                uint32_t bad = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) bad |= (__float_as_uint(v[q][r].y) >> 31) ^ flag;
+                if (!bad) break;
+                __nanosleep(64);                                                  // (slices still missing: poll at a low rate)
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float mu = 0.f, M2 = 0.f;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) mu = fmaf(tab_s[32 + 8 * sb + r].y, v[q][r].x, mu);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float dd = v[q][r].x - mu;
+                    M2 += fmaf(tab_s[32 + 8 * sb + r].x * dd, dd, __uint_as_float(__float_as_uint(v[q][r].y) & 0x7fffffffu));
                 }
+                pbuf[(o * 3 + sb) * CH + 32 * q + lane] = make_float2(mu, M2);
+            }
+            nbar_sync(NB_STATW, FSTAT_THREADS);
+            for (int rep = 0; rep < nrep; ++rep) {
+                const int c = rep ? 96 + lane : 32 * sb + lane;
+                float2 q[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) q[k] = pbuf[(o * 3 + k) * CH + c];
                 float m = 0.f, M2 = 0.f;
 #pragma unroll
-                for (int r = 0; r < FCS; ++r) m = fmaf(tab_s[4 + r].y, v[r].x, m);
+                for (int k = 0; k < 3; ++k) m = fmaf(tab_s[56 + k].y, q[k].x, m);
 #pragma unroll
-                for (int r = 0; r < FCS; ++r) {
-                    const float dd = v[r].x - m;
-                    M2 += fmaf(tab_s[4 + r].x * dd, dd, __uint_as_float(__float_as_uint(v[r].y) & 0x7fffffffu));
+                for (int k = 0; k < 3; ++k) {
+                    const float dd = q[k].x - m;
+                    M2 += fmaf(tab_s[56 + k].x * dd, dd, q[k].y);
                 }
                 const float var = M2 * inv_em1;
-                stat_s[sig * CH + c] = make_float2(m, 1.0f / sqrtf(var + 1e-3f));
+                const float2 st = make_float2(m, rsqrtf(var + 1e-3f));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pbuf[(o * 3 + k) * CH + c] = st;
             }
-            nbar_arrive(NB_STAT0 + sig, NB_THREADS);
-            TR(2, 730 + sig);
-            ++ecount;
-            if (sig) ++sxc1; else ++sxc0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + BAR_STAT0 + o);
+            TR(2, 730 + o);
+            sxc = (sxc & ~(3u << (2 * o))) | (((((sxc >> (2 * o)) & 3u) + 1u) & 3u) << (2 * o));
         };
         if (nd > 0) {
-            const uint32_t* src = w_src(dual_net(0) * nphase);
-            w_load(src, 0);
+            const int mat = round_net(0) * nphase;
+            w_load(mat, 0);
             w_store(0);
-            w_load(src, 1);
+            w_load(mat, 1);
             w_store(1);
             w_publish();
         }
         for (int64_t d = 0; d < nd; ++d) {
-            const int mat_base = dual_net(d) * nphase;
-            for (int ph = 0; ph <= nphase; ++ph) {            // (ph == nphase: only the last layer's second statistics event)
+            const int mat_base = round_net(d) * nphase;
+            for (int ph = 0; ph <= nphase; ++ph) {            // (ph == nphase: only the last layer's last statistics event)
                 if (warp == FCONV_WARPS) {
                     if (ph == nphase) break;
                     TR(1, 10);
                     mbar_wait(bar + BAR_WREADY, wpar);
                     tc_fence_after();
                     TR(1, 11);
-                    for (int sig = 0; sig < 2; ++sig) {
-                        for (int s = 0; s < nsub; ++s, ++g) {
-                            const uint32_t b = g & 1u;
-                            TR(1, 100 + 10 * sig + s);
-                            mbar_wait(bar + BAR_FULL0 + b, (fpar >> b) & 1u);
-                            fpar ^= 1u << b;
-                            tc_fence_after();
-                            TR(1, 200 + 10 * sig + s);
-                            if (elect_one()) {
-                                const uint32_t b_hi = smem_u32(Bbuf) + b * 2 * FB_PART;
-                                // (N is a multiple of 16: a last sub-tile of 8 or 24 edges computes 8 columns nobody reads)
-                                issue_sub_gemm(tmem_base + FT_SLOT * sig + FSUB * s, tmem_base + FT_W, tmem_base + FT_W + 64, b_hi,
-                                               b_hi + FB_PART, min(FSUB, (ES - FSUB * s + 15) & ~15));
-                                umma_commit(bar + BAR_DONE0 + b);
-                                if (sig == 1 && s == nsub - 1) umma_commit(bar + BAR_PDONE);
-                            }
-                            __syncwarp();
+                    for (int t = 0; t < ntile; ++t, ++g) {
+                        const uint32_t b = g & 1u;
+                        TRF(1, 100 + t);
+                        mbar_wait(bar + BAR_FULL0 + b, (fpar >> b) & 1u);
+                        fpar ^= 1u << b;
+                        tc_fence_after();
+                        TR(1, 200 + t);
+                        if (elect_one()) {
+                            const uint32_t b_hi = smem_u32(Bbuf) + b * 2 * FB_PART;
+                            issue_sub_gemm(tmem_base + FSUB * t, tmem_base + FT_W, tmem_base + FT_W + 64, b_hi, b_hi + FB_PART, FSUB);
+                            umma_commit(bar + BAR_DONE0 + b);
+                            if (t == ntile - 1) umma_commit(bar + BAR_PDONE);
                         }
+                        __syncwarp();
                     }
                 } else {
-                    // layer outputs in the order the converters complete them: (half 1, ph - 1) during this layer's first half,
-                    // (half 0, ph) during its second half
-                    for (int ev = ph > 0 ? 0 : 1; ev < (ph < nphase ? 2 : 1); ++ev) stat_event(ev ^ 1);
+                    // layer outputs in the order the converters complete them: object 2 of the previous layer during this layer's
+                    // first tiles, then objects 0 and 1 of this layer.  Object 1's exchange overlaps the end of the layer, where
+                    // the next weights are due: they go first, the slices are collected afterwards.
+                    if (ph > 0) {
+                        ev_publish(2);
+                        ev_finish(2);
+                    }
                     if (ph == nphase) break;
+                    ev_publish(0);
+                    ev_finish(0);
+                    ev_publish(1);
                 }
                 wpar ^= 1u;
                 // next layer's weights: first half fetched while this layer's last MMAs drain
                 const bool last_ph = ph + 1 == nphase;
                 const bool more = !last_ph || d + 1 < nd;
                 if (more) {
-                    const uint32_t* src = w_src(last_ph ? dual_net(d + 1) * nphase : mat_base + ph + 1);
-                    w_load(src, 0);
+                    const int mat = last_ph ? round_net(d + 1) * nphase : mat_base + ph + 1;
+#ifdef DCD_EXP_NO_WRELOAD
+                    (void)mat;
+                    mbar_wait(bar + BAR_PDONE, ppar);
+                    tc_fence_after();
+                    w_publish();
+#else
+                    w_load(mat, 0);
                     TR(warp == FCONV_WARPS ? 1 : 2, 20);
-                    mbar_wait_relaxed(bar + BAR_PDONE, ppar);
+                    mbar_wait(bar + BAR_PDONE, ppar);
                     tc_fence_after();
                     TR(warp == FCONV_WARPS ? 1 : 2, 21);
                     w_store(0);
-                    w_load(src, 1);
+                    w_load(mat, 1);
                     w_store(1);
                     w_publish();
+#endif
                     TR(warp == FCONV_WARPS ? 1 : 2, 22);
                 } else {
-                    mbar_wait_relaxed(bar + BAR_PDONE, ppar);
+                    mbar_wait(bar + BAR_PDONE, ppar);
                 }
                 ppar ^= 1u;
+                if (warp != FCONV_WARPS) ev_finish(1);
             }
         }
     } else {
         // =====================================================================================================
         // converter warps: thread = channel; units of 16 edges; produce the B operands, consume the accumulators
         // =====================================================================================================
-        const int wg = warp >> 2;                             // unit inside a sub-tile
+        const int wg = warp >> 2;                             // unit stream: this warp converts the units u with u % 3 == wg
         const int e_base = (int)rank * ES;
-        const int valid = max(0, min(ES, E - e_base));
-        uint32_t g = 0;                                       // running sub-tile step (same sequence as the MMA warp)
+        const int valid = max(0, min(ES, E - e_base));        // valid edges of this CTA's slice (the same for the three objects)
+        uint32_t g = 0;                                       // running tile step (same sequence as the MMA warp)
         uint32_t par = 0, pend = 0;                           // per operand buffer: next wait parity, MMA in flight
         auto wait_buf = [&](uint32_t b) {
             if ((pend >> b) & 1u) {
@@ -516,29 +582,32 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 tc_fence_after();
             }
         };
-        uint32_t fcount = 0;                                  // finalisations done (alternates the partials buffer)
-        const float inv_cnt_wg = tab_s[wg].x > 0.f ? 1.0f / tab_s[wg].x : 0.f;
+        auto obj_of = [&](int u) { return (u >= upo ? 1 : 0) + (u >= 2 * upo ? 1 : 0); };
+        uint32_t spar = 0;                                    // wait parities of the three statistics barriers (this warp's view)
+        uint32_t mine = 0;                                    // objects this warp has a unit of (all three unless the slices are tiny)
+        for (int u = wg; u < FOBJ * upo; u += 3) mine |= 1u << obj_of(u);
+        // unit stream of this warp's units of object o: (wg - o * upo) mod 3
+        auto stream_of = [&](int o) { return (wg + 3 * o * upo - o * upo) % 3; };
 
         for (int64_t d = 0; d < nd; ++d) {
-            const int64_t pair = dual_pair(d);
-            const int net = dual_net(d);
-            const int64_t objA = 2 * pair;
-            const bool validB = 2 * pair + 1 < L.N;
-            const int64_t objB = validB ? objA + 1 : objA;
+            const int64_t trip = round_trip(d);
+            const int net = round_net(d);
+            const int64_t obj0 = FOBJ * trip;                 // objects obj0 + o, clamped to the last one
             const int cin = net == 0 ? 4 : 6;
             const float* __restrict__ prm = a.params[net];
             const int mat_base = net * nphase;
 
-            // ---- edge features of the two slices, staged in the (idle) operand buffers: f_s[2][6][ES]
+            // ---- edge features of the three slices, staged in the (idle) operand buffers: f_s[3][6][ES]
+            TR(0, 900);
             wait_buf(0);
             wait_buf(1);
             conv_sync();
             float* f_s = reinterpret_cast<float*>(Bbuf);
-            if (tid < 2 * ES) {
-                const int sig = tid >= ES ? 1 : 0;
-                const int el = tid - sig * ES;
+            if (tid < FOBJ * ES) {
+                const int o = obj_of(tid >> 4);
+                const int el = tid - o * ES;
                 const int e = e_base + el;
-                const int64_t obj = sig ? objB : objA;
+                const int64_t obj = min(obj0 + o, L.N - 1);
                 int i, j;
                 decode_edge(e < E ? e : E - 1, L.n, i, j);
                 float f[6];
@@ -553,7 +622,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     f[3] = __ldg(pj); f[4] = __ldg(pj + 1); f[5] = __ldg(pj + 2);
                 }
 #pragma unroll
-                for (int r = 0; r < 6; ++r) f_s[(sig * 6 + r) * ES + el] = f[r];
+                for (int r = 0; r < 6; ++r) f_s[(o * 6 + r) * ES + el] = f[r];
             }
             conv_sync();
             // ---- conv_in: X0 = W_in . f + b_in   (the features are warp-wide broadcasts)
@@ -562,60 +631,49 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
 #pragma unroll
                 for (int q = 0; q < 6; ++q) wq[q] = (q < cin) ? __ldg(prm + blob_in_w() + q * CH + ch) : 0.f;
                 const float b = __ldg(prm + blob_in_b(cin) + ch);
-                for (int sig = 0; sig < 2; ++sig) {
-                    const float* fo = f_s + sig * 6 * ES;
-                    for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
+                for (int u = wg; u < FOBJ * upo; u += 3) {
+                    const int o = obj_of(u);
+                    const int lc = 16 * (u - o * upo);
+                    const float* fo = f_s + o * 6 * ES + lc;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            if ((col0 >> 2) + q4 >= xrows) break;
-                            float x[4];
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float x[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int e = col0 + 4 * q4 + i;
-                                float acc = b;
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = 4 * q4 + i;
+                            float acc = b;
 #pragma unroll
-                                for (int r = 0; r < 6; ++r) acc = fmaf(wq[r], fo[r * ES + e], acc);
-                                x[i] = (e < valid) ? acc : 0.f;
-                            }
-                            Xs[(sig * xrows + (col0 >> 2) + q4) * CH + ch] = make_float4(x[0], x[1], x[2], x[3]);
+                            for (int r = 0; r < 6; ++r) acc = fmaf(wq[r], fo[r * ES + e], acc);
+                            x[i] = (lc + e < valid) ? acc : 0.f;
                         }
+                        Xs[(4 * u + q4) * CH + ch] = make_float4(x[0], x[1], x[2], x[3]);
                     }
                 }
             }
             conv_sync();                                      // the features are consumed: operand buffers free
+            TR(0, 901);
 
-            // ---- the layers.  Stream of steps (layer, half, sub-tile); the two halves alternate per layer, so the statistics
-            //      exchange of one object's layer (drain of its last MMAs, L2 round trip between the 16 CTAs) is hidden behind
-            //      the other object's steps.
+            // ---- the layers: a stream of steps (layer, tile)
             float un_out = 0.f, b_out = 0.f, un_prev = 0.f, b_prev = 0.f;   // scale / bias of the matrices of this and the previous layer
+            float un_next = __ldg(scales + mat_base).y, b_next = __ldg(bias2 + mat_base * CH + ch);       // (fetched one layer ahead)
             int ph_now = 0;
-            int qa = -1, qb = -1;                             // sub-tiles whose statistics are due (older, newer): s | half << 8 | (layer & 1) << 9 | buffer << 10
-            int fin0 = 0, fin1 = 0;                           // layers whose statistics are final (published), per half
-            float K = 0.f, s1 = 0.f, s2 = 0.f, bK = 0.f;      // shifted sums of the layer output being accumulated
+            int qa = -1, qb = -1;                             // tiles whose statistics are due (older, newer): tile | (layer & 1) << 9 | buffer << 10
+            int fin = 0;                                      // layers whose partial is posted, per object (8 bits each)
+            int o_post = 0;                                   // next object to post in the layer whose statistics are being accumulated
+            float K = 0.f, s1 = 0.f, s2 = 0.f, bK = 0.f;      // shifted sums of the layer output being accumulated (one object at a time)
             bool have_K = false;
             bool cv_ready = false;                            // the next unit's accumulators are already in flight
             uint32_t cv[16], sv[16];
 
-            // statistics of one unit from its raw accumulators (un, bb: scale and bias of the producing matrix)
+            // statistics of one unit from its raw accumulators (un, bb: scale and bias of the producing matrix), as sums shifted
+            // by K = the object's first value seen by this thread
             auto stats_math = [&](const uint32_t (&raw)[16], int nv, float un, float bb) {
-                if (!have_K) {                                // first unit: choose the shift K = mean of this unit
-                    float v[16], sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] = fmaf(__uint_as_float(raw[i]), un, bb);
-                        if (i < nv) sum += v[i];
-                    }
-                    K = sum / (float)nv;
+                if (!have_K) {
+                    K = fmaf(__uint_as_float(raw[0]), un, bb);
                     bK = bb - K;
                     have_K = true;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (i < nv) {
-                            const float dd = v[i] - K;
-                            s1 += dd;
-                            s2 = fmaf(dd, dd, s2);
-                        }
-                } else if (nv == 16) {
+                }
+                if (nv == 16) {
                     float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
@@ -639,291 +697,294 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                         }
                 }
             };
-            // one layer output of half `sig` is complete: hand this unit stream's (mean, M2) to the statistics warps (which merge,
-            // publish, collect the 15 other slices of the group and post (mean, rstd) of the layer: see the service warps)
-            auto finalize = [&](int sig) {
-                float2* pbuf = part2_s + (fcount & 1u) * 3 * CH;
-                const float m = K + s1 * inv_cnt_wg;
-                const float M2 = fmaxf(fmaf(-s1 * inv_cnt_wg, s1, s2), 0.f);
-                pbuf[wg * CH + ch] = make_float2(m, M2);
-                nbar_arrive(NB_PART, NB_THREADS);
+            // this unit stream's part of object o's layer output is complete (possibly empty): post its (mean, M2) for the
+            // statistics warps
+            auto post = [&](int o) {
+                const int k = stream_of(o);
+                const float ic = tab_s[9 + o * 3 + k].x;
+                const float m = K + s1 * ic;
+                const float M2 = fmaxf(fmaf(-s1 * ic, s1, s2), 0.f);
+                pbuf[(o * 3 + k) * CH + ch] = make_float2(m, M2);
+                nbar_arrive(NB_PART0 + o, NB_THREADS);
                 TR(0, 603);
                 K = 0.f; s1 = 0.f; s2 = 0.f; bK = 0.f;
                 have_K = false;
-                ++fcount;
-                if (sig) ++fin1; else ++fin0;
+                fin += 1 << (8 * o);
             };
-            // statistics of the oldest pending sub-tile; `wait`: its MMA is not yet known to be complete; `loaded`: its accumulators
+            // (mean, rstd) of object o's latest layer, handed back by the statistics warps in this warp's partial slot
+            auto collect = [&](int o) {
+                TR(0, 606);
+#ifndef DCD_EXP_NO_STATWAIT
+                mbar_wait_backoff(bar + BAR_STAT0 + o, (spar >> o) & 1u, 40);
+#endif
+                spar ^= 1u << o;
+                TR(0, 608);
+                return pbuf[(o * 3 + stream_of(o)) * CH + ch];
+            };
+
+            // statistics of the oldest pending tile; `wait`: its MMA is not yet known to be complete; `loaded`: its accumulators
             // are already in sv (loaded and waited for by the step)
             auto process_oldest = [&](bool wait, bool loaded) {
                 const int e = qa;
                 qa = qb;
                 qb = -1;
-                const int s_e = e & 0xff, sig_e = (e >> 8) & 1, pp = (e >> 9) & 1;
+                const int t_e = e & 0xff, pp = (e >> 9) & 1;
                 if (wait) wait_buf((uint32_t)(e >> 10) & 1u);
-                const int col = FSUB * s_e + 16 * wg;
-                const int nv = min(16, valid - col);
+                const int u_e = 3 * t_e + wg;
+                const int o_e = obj_of(u_e);
+                const int lc = 16 * (u_e - o_e * upo);
+                const int nv = min(16, valid - lc);
+                if (t_e == 0) o_post = 0;
+                const int layer_e = (pp == (ph_now & 1)) ? ph_now : ph_now - 1;
+                // (objects this stream has no unit of: an empty partial, once the previous layer's exchange of that object is over)
+                auto post_any = [&](int o) {
+                    if (!((mine >> o) & 1u) && layer_e > 0) (void)collect(o);
+                    post(o);
+                };
+                while (o_post < o_e) post_any(o_post++);
                 if (nv > 0) {
                     if (!loaded) {
-                        tmem_ld16_issue(t_lane + FT_SLOT * sig_e + col, sv);
+                        tmem_ld16_issue(t_lane + 16 * u_e, sv);
                         tmem_ld16_wait(sv);
                     }
                     const bool cur = pp == (ph_now & 1);
                     stats_math(sv, nv, cur ? un_out : un_prev, cur ? b_out : b_prev);
                 }
-                if (s_e == nsub - 1) finalize(sig_e);
+                const int o_nx = (t_e + 1 < ntile) ? obj_of(u_e + 3) : FOBJ;
+                while (o_post < o_nx) post_any(o_post++);
             };
-            auto ensure_finalized = [&](int sig, int need) {
-                while ((sig ? fin1 : fin0) < need && qa >= 0) process_oldest(true, false);
+            auto ensure_posted = [&](int o, int need) {
+                while (((fin >> (8 * o)) & 0xff) < need && qa >= 0) process_oldest(true, false);
             };
-            // (mean, rstd) of the latest finalised layer of half `sig`, posted by the statistics warps
-            auto collect = [&](int sig) {
-                TR(0, 606);
-                nbar_sync(NB_STAT0 + sig, NB_THREADS);
-                TR(0, 608);
-                return stat_s[sig * CH + ch];
-            };
-
-            float fin_a0 = 0.f, fin_c0 = 0.f, fin_a1 = 0.f, fin_c1 = 0.f;    // the final features' transform per half
-            for (int ph = 0; ph <= nphase; ++ph) {            // (ph == nphase: only the last layer's statistics are collected)
+            int o_cur = -1;                                   // object of the current input transform
+            float a_in = 0.f, c_in = 0.f;
+            for (int ph = 0; ph < nphase; ++ph) {
                 const int kind = (ph & 1) ? 2 : 0;            // 0: (residual update ->) folded preconv.conv1, 2: conv2
                 ph_now = ph;
                 un_prev = un_out;
                 b_prev = b_out;
-                if (ph < nphase) {
-                    un_out = __ldg(scales + mat_base + ph).y;
-                    b_out = __ldg(bias2 + (mat_base + ph) * CH + ch);
+                un_out = un_next;
+                b_out = b_next;
+                if (ph + 1 < nphase) {
+                    un_next = __ldg(scales + mat_base + ph + 1).y;
+                    b_next = __ldg(bias2 + (mat_base + ph + 1) * CH + ch);
                 }
                 const bool reads_d = ph > 0;
-                for (int sig = 0; sig < 2; ++sig) {
-                    // input transform of this layer as one FMA on the raw accumulator: the context norm of the producing
-                    // layer folded in ((d*un + b - mean) * rstd)
-                    float a_in = 0.f, c_in = 0.f;
-                    if (reads_d) {
-                        ensure_finalized(sig, ph);
-                        const float2 st = collect(sig);
+                o_cur = -1;
+                // Software pipeline over the steps: the accumulators of the NEXT unit to convert (cv) and of the unit whose
+                // statistics are due (sv, two steps behind: its MMA is known complete when its operand buffer comes free)
+                // are in flight from tensor memory while the current unit is being processed.
+                for (int t = 0; t < ntile; ++t, ++g) {
+                    const int u = 3 * t + wg;                 // this warp's unit: columns [16 u, 16 u + 16) of the CTA
+                    const int o = obj_of(u);
+                    const int lc = 16 * (u - o * upo);        // first edge of the unit inside the object's slice
+                    if (reads_d && o != o_cur) {
+                        // input transform of this layer as one FMA on the raw accumulator: the context norm of the producing
+                        // layer folded in ((d*un + b - mean) * rstd)
+                        ensure_posted(o, ph);
+                        const float2 st = collect(o);
                         a_in = un_prev * st.y;
                         c_in = (b_prev - st.x) * st.y;
+                        o_cur = o;
                     }
-                    if (ph == nphase) {
-                        if (sig) { fin_a1 = a_in; fin_c1 = c_in; } else { fin_a0 = a_in; fin_c0 = c_in; }
-                        continue;
+                    const uint32_t b = g & 1u;
+                    TR(0, 1000 * kind + 100 + t);
+                    wait_buf(b);
+                    TRF(0, 1000 * kind + 200 + t);
+                    unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
+                    if (reads_d && !cv_ready) tmem_ld16_issue(t_lane + 16 * u, cv);
+                    // the tile of two steps ago (same operand buffer: its MMA is complete) is due for its statistics
+                    const bool due = qb >= 0;
+                    bool st_load = false;
+                    if (due) {
+                        const int u_e = 3 * (qa & 0xff) + wg;
+                        st_load = valid > 16 * (u_e - obj_of(u_e) * upo);
                     }
-                    const uint32_t t_half = t_lane + FT_SLOT * sig;
-                    float4* Xh = Xs + (size_t)(sig * xrows) * CH + ch;
-                    // Software pipeline over the steps: the accumulators of the NEXT unit to convert (cv) and of the unit whose
-                    // statistics are due (sv, two steps behind: its MMA is known complete when its operand buffer comes free)
-                    // are in flight from tensor memory while the current unit is being processed.
-                    for (int s = 0; s < nsub; ++s, ++g) {
-                        const uint32_t b = g & 1u;
-                        TR(0, 1000 * kind + 100 + 10 * sig + s);
-                        wait_buf(b);
-                        TR(0, 1000 * kind + 200 + 10 * sig + s);
-                        unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
-                        const int col0 = FSUB * s + 16 * wg;
-                        const bool active = col0 < ES;
-                        const int rows = min(4, xrows - (col0 >> 2));         // float4 rows of this unit inside the slice (last unit: 2)
-                        if (reads_d && active && !cv_ready) tmem_ld16_issue(t_half + col0, cv);
-                        // the sub-tile of two steps ago (same operand buffer: its MMA is complete) is due for its statistics
-                        const bool due = qb >= 0;
-                        bool st_load = false;
-                        if (due) {
-                            const int col = FSUB * (qa & 0xff) + 16 * wg;
-                            st_load = valid > col;
-                        }
-                        float v[16];
-                        float4* Xp = Xh + (col0 >> 2) * CH;
-                        float4 x4[4];
-                        if (active && kind == 0) {
+                    float v[16];
+                    float4* Xp = Xs + (4 * u) * CH + ch;
+                    float4 x4[4];
+                    if (kind == 0) {
 #pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) x4[q4] = (q4 < rows) ? Xp[q4 * CH] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                        if (reads_d && active) tmem_ld16_wait(cv);
-                        cv_ready = false;
-                        TR(0, 1000 * kind + 300 + 10 * sig + s);
-                        if (st_load) tmem_ld16_issue(t_lane + FT_SLOT * ((qa >> 8) & 1) + FSUB * (qa & 0xff) + 16 * wg, sv);
-                        if (active) {
-                            if (kind == 0) {
-                                if (reads_d) {
+                        for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                    }
+                    if (reads_d) tmem_ld16_wait(cv);
+                    cv_ready = false;
+                    TRF(0, 1000 * kind + 300 + t);
+                    if (st_load) tmem_ld16_issue(t_lane + 16 * (3 * (qa & 0xff) + wg), sv);
+                    if (kind == 0) {
+                        if (reads_d) {
 #pragma unroll
-                                    for (int i = 0; i < 16; i += 2) {
-                                        ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
-                                        v[i] = fmaxf(v[i], 0.f);
-                                        v[i + 1] = fmaxf(v[i + 1], 0.f);
-                                    }
-#pragma unroll
-                                    for (int q4 = 0; q4 < 4; ++q4) {
-                                        fadd2_acc(v[4 * q4], v[4 * q4 + 1], x4[q4].x, x4[q4].y);
-                                        fadd2_acc(v[4 * q4 + 2], v[4 * q4 + 3], x4[q4].z, x4[q4].w);
-                                    }
-                                    if (col0 + 16 > valid) {
-#pragma unroll
-                                        for (int i = 0; i < 16; ++i)
-                                            if (col0 + i >= valid) v[i] = 0.f;
-                                    }
-#pragma unroll
-                                    for (int q4 = 0; q4 < 4; ++q4)
-                                        if (q4 < rows) Xp[q4 * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                                } else {
-#pragma unroll
-                                    for (int q4 = 0; q4 < 4; ++q4) {
-                                        v[4 * q4] = x4[q4].x; v[4 * q4 + 1] = x4[q4].y; v[4 * q4 + 2] = x4[q4].z; v[4 * q4 + 3] = x4[q4].w;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 2)
-                                    ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
+                            for (int i = 0; i < 16; i += 2) {
+                                ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
+                                v[i] = fmaxf(v[i], 0.f);
+                                v[i + 1] = fmaxf(v[i + 1], 0.f);
                             }
-                            store_unit(b_hi, b_hi + FB_PART, ch, wg, v);
-                        }
-                        TR(0, 1000 * kind + 400 + 10 * sig + s);
-                        fence_async_smem();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar + BAR_FULL0 + b);
-                        pend |= 1u << b;
-                        TR(0, 1000 * kind + 500 + 10 * sig + s);
-                        // the next unit to convert: next sub-tile of this half, else the other half's first (whose producing MMAs
-                        // are complete when this segment has at least two steps)
-                        {
-                            const bool cross = s + 1 == nsub;
-                            const int nsig = cross ? (sig ^ 1) : sig;
-                            const int nph = (cross && sig == 1) ? ph + 1 : ph;
-                            const int ncol = cross ? 16 * wg : col0 + FSUB;
-                            if (st_load) tmem_ld16_wait(sv);          // (before the next load is issued: the wait covers all loads in flight)
-                            TR(0, 1000 * kind + 550 + 10 * sig + s);
-                            if (nph > 0 && nph < nphase && ncol < ES && (!cross || nsub >= 2)) {
-                                tmem_ld16_issue(t_lane + FT_SLOT * nsig + ncol, cv);
-                                cv_ready = true;
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                fadd2_acc(v[4 * q4], v[4 * q4 + 1], x4[q4].x, x4[q4].y);
+                                fadd2_acc(v[4 * q4 + 2], v[4 * q4 + 3], x4[q4].z, x4[q4].w);
+                            }
+                            if (lc + 16 > valid) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (lc + i >= valid) v[i] = 0.f;
+                            }
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4)
+                                Xp[q4 * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                v[4 * q4] = x4[q4].x; v[4 * q4 + 1] = x4[q4].y; v[4 * q4 + 2] = x4[q4].z; v[4 * q4 + 3] = x4[q4].w;
                             }
                         }
-                        if (due) process_oldest(false, true);
-                        TR(0, 1000 * kind + 570 + 10 * sig + s);
-                        const int ent = s | (sig << 8) | ((ph & 1) << 9) | ((int)b << 10);
-                        if (qa < 0) qa = ent; else qb = ent;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2)
+                            ffma2_bc(v[i], v[i + 1], __uint_as_float(cv[i]), __uint_as_float(cv[i + 1]), a_in, c_in);
                     }
+                    store_unit(b_hi, b_hi + FB_PART, ch, wg, v);
+                    TRF(0, 1000 * kind + 400 + t);
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar + BAR_FULL0 + b);
+                    pend |= 1u << b;
+                    TRF(0, 1000 * kind + 500 + t);
+                    if (st_load) tmem_ld16_wait(sv);              // (before the next load is issued: the wait covers all loads in flight)
+                    // the next unit to convert: the next tile's, else the next layer's first (whose producing MMA is complete
+                    // when a layer has at least two tiles)
+                    {
+                        const bool cross = t + 1 == ntile;
+                        const int nu = cross ? wg : u + 3;
+                        const int nph = cross ? ph + 1 : ph;
+                        if (nph > 0 && nph < nphase && (!cross || ntile >= 2)) {
+                            tmem_ld16_issue(t_lane + 16 * nu, cv);
+                            cv_ready = true;
+                        }
+                    }
+                    if (due) process_oldest(false, true);
+                    const int ent = t | ((ph & 1) << 9) | ((int)b << 10);
+                    if (qa < 0) qa = ent; else qb = ent;
                 }
             }
             TR(0, 600);
 
-            // ---- final features x = relu(cn(Y2)) + X of both halves (all MMAs are complete: the operand buffers are free)
+            // ---- final features x = relu(cn(Y2)) + X of the three objects.  First the statistics still due (their MMAs are then
+            //      complete and the operand buffers free for the epilogue's scratch).
+            ph_now = nphase;
+            un_prev = un_out;
+            b_prev = b_out;
+            while (qa >= 0) process_oldest(true, false);
             TR(0, 601);
+            o_cur = -1;
+            float a_fin = 0.f, c_fin = 0.f;
             int itn = 0;
-            for (int sig = 0; sig < 2; ++sig) {
-                const float a_fin = sig ? fin_a1 : fin_a0, c_fin = sig ? fin_c1 : fin_c0;
-                const int64_t obj = sig ? objB : objA;
-                const bool emit = sig == 0 || validB;
-                const uint32_t t_half = t_lane + FT_SLOT * sig;
-                const float4* Xh = Xs + (size_t)(sig * xrows) * CH + ch;
-                auto final_unit = [&](int col0, float (&v)[16]) {
-                    const float4* Xp = Xh + (col0 >> 2) * CH;
-                    const int rows = min(4, xrows - (col0 >> 2));
+            for (int u = wg; u < FOBJ * upo; u += 3, ++itn) {
+                const int o = obj_of(u);
+                const int lc = 16 * (u - o * upo);
+                if (o != o_cur) {
+                    const float2 st = collect(o);
+                    a_fin = un_out * st.y;
+                    c_fin = (b_out - st.x) * st.y;
+                    o_cur = o;
+                }
+                const bool emit = obj0 + o < L.N;
+                const int64_t obj = min(obj0 + o, L.N - 1);
+                float v[16];
+                {
+                    const float4* Xp = Xs + (4 * u) * CH + ch;
                     float4 x4[4];
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) x4[q4] = (q4 < rows) ? Xp[q4 * CH] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    tmem_ld16(t_half + col0, v);
+                    for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
+                    tmem_ld16(t_lane + 16 * u, v);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], a_fin, c_fin), 0.f);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         v[4 * q4] += x4[q4].x; v[4 * q4 + 1] += x4[q4].y; v[4 * q4 + 2] += x4[q4].z; v[4 * q4 + 3] += x4[q4].w;
                     }
-                    if (col0 + 16 > valid) {
+                    if (lc + 16 > valid) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (col0 + i >= valid) v[i] = 0.f;
+                            if (lc + i >= valid) v[i] = 0.f;
                     }
-                };
+                }
                 if (!paired) {
                     // -> global, channel-major [obj][128][EP] (consumed by gmw_edge_weight_kernel / the correspondence branch)
-                    float* G = act_ptr(a.ws, L, net, 0, SLOT_X) + obj * (int64_t)CH * EP + (int64_t)ch * EP + e_base;
-                    for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
-                        float v[16];
-                        final_unit(col0, v);
-                        const int rows = min(4, xrows - (col0 >> 2));
+                    float* G = act_ptr(a.ws, L, net, 0, SLOT_X) + obj * (int64_t)CH * EP + (int64_t)ch * EP;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4)
-                            if (emit && q4 < rows)
-                                __stcs(reinterpret_cast<float4*>(G + col0 + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));   // streamed: keep the weight image in L2
-                    }
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        if (emit && e_base + lc + 4 * q4 < EP)
+                            __stcs(reinterpret_cast<float4*>(G + e_base + lc + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));   // streamed: keep the weight image in L2
                 } else if (net == 0) {
-                    // park the 4-d net's features in this CTA's slice of an L2-resident scratch ([2][ES/4][128] float4 like Xs; the
-                    // 16 CTAs of a group fill exactly two objects' worth of the workspace slot, EP = 16 ES): the thread that
-                    // writes a word is the one that reads it back after the 6-d net, so no fence or barrier is needed
-                    float4* Pk = park + ((size_t)blockIdx.x * 2 * xrows + (size_t)sig * xrows) * CH + ch;
-                    for (int col0 = 16 * wg; col0 < ES; col0 += FSUB) {
-                        float v[16];
-                        final_unit(col0, v);
-                        const int rows = min(4, xrows - (col0 >> 2));
+                    // park the 4-d net's features in this CTA's slice of an L2-resident scratch ([3 ES / 4][128] float4 like Xs):
+                    // the thread that writes a word is the one that reads it back after the 6-d net, so no fence or barrier is needed
+                    float4* Pk = park + ((size_t)blockIdx.x * (4 * FOBJ * upo) + 4 * u) * CH + ch;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4)
-                            if (q4 < rows) Pk[((col0 >> 2) + q4) * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                    }
+                    for (int q4 = 0; q4 < 4; ++q4) Pk[q4 * CH] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
                 } else {
                     // edge weights straight from the two nets' final features (GMW/model/model.py:176-181, diagonal of pairwiseL2Dist):
                     // per edge the three channel sums |a|^2, |c|^2, a.c — 32 channels by a halving shuffle tree, the 4 lane quarters
                     // through shared memory (the operand buffers are idle here) — then
                     //   w = 1 / sqrt(max((|c^|^2 - 2 a^.c^) + |a^|^2, 1e-30)),  a^ = a / max(|a|, 1e-12)
-                    const float4* Pk = park + ((size_t)blockIdx.x * 2 * xrows + (size_t)sig * xrows) * CH + ch;
+                    const float4* Pk = park + ((size_t)blockIdx.x * (4 * FOBJ * upo) + 4 * u) * CH + ch;
                     float* red = reinterpret_cast<float*>(Bbuf) + wg * (2 * 4 * 48);      // [2 buffers][4 quarters][16 edges][3]
-                    float* W = reg_w + obj * (int64_t)E + e_base;
-                    for (int col0 = 16 * wg; col0 < ES; col0 += FSUB, ++itn) {
-                        float cvv[16], aa[16], cc[16], ac[16];
-                        final_unit(col0, cvv);
-                        const int rows = min(4, xrows - (col0 >> 2));
+                    float* W = reg_w + obj * (int64_t)E + e_base + lc;
+                    float aa[16], cc[16], ac[16];
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const float4 p = (q4 < rows) ? Pk[((col0 >> 2) + q4) * CH] : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float av[4] = {p.x, p.y, p.z, p.w};
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float4 p = Pk[q4 * CH];
+                        const float av[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float c = cvv[4 * q4 + i];
-                                aa[4 * q4 + i] = __fmul_rn(av[i], av[i]);          // (explicit roundings: gmw_edge_weight_kernel<true>
-                                cc[4 * q4 + i] = __fmul_rn(c, c);                  //  replays this exact sequence)
-                                ac[4 * q4 + i] = __fmul_rn(av[i], c);
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const float c = v[4 * q4 + i];
+                            aa[4 * q4 + i] = __fmul_rn(av[i], av[i]);          // (explicit roundings: gmw_edge_weight_kernel<true>
+                            cc[4 * q4 + i] = __fmul_rn(c, c);                  //  replays this exact sequence)
+                            ac[4 * q4 + i] = __fmul_rn(av[i], c);
                         }
-                        // halving tree over the 32 lanes: afterwards lane l holds the sums of edge l >> 1
+                    }
+                    // halving tree over the 32 lanes: afterwards lane l holds the sums of edge l >> 1
 #pragma unroll
-                        for (int h = 8; h >= 1; h >>= 1) {
-                            const bool up = (lane & (2 * h)) != 0;
+                    for (int h = 8; h >= 1; h >>= 1) {
+                        const bool up = (lane & (2 * h)) != 0;
 #pragma unroll
-                            for (int k = 0; k < h; ++k) {
-                                const float sa = up ? aa[k] : aa[k + h], sc = up ? cc[k] : cc[k + h], sx = up ? ac[k] : ac[k + h];
-                                const float ka = up ? aa[k + h] : aa[k], kc = up ? cc[k + h] : cc[k], kx = up ? ac[k + h] : ac[k];
-                                aa[k] = __fadd_rn(ka, __shfl_xor_sync(0xffffffffu, sa, 2 * h));
-                                cc[k] = __fadd_rn(kc, __shfl_xor_sync(0xffffffffu, sc, 2 * h));
-                                ac[k] = __fadd_rn(kx, __shfl_xor_sync(0xffffffffu, sx, 2 * h));
-                            }
+                        for (int k = 0; k < h; ++k) {
+                            const float sa = up ? aa[k] : aa[k + h], sc = up ? cc[k] : cc[k + h], sx = up ? ac[k] : ac[k + h];
+                            const float ka = up ? aa[k + h] : aa[k], kc = up ? cc[k + h] : cc[k], kx = up ? ac[k + h] : ac[k];
+                            aa[k] = __fadd_rn(ka, __shfl_xor_sync(0xffffffffu, sa, 2 * h));
+                            cc[k] = __fadd_rn(kc, __shfl_xor_sync(0xffffffffu, sc, 2 * h));
+                            ac[k] = __fadd_rn(kx, __shfl_xor_sync(0xffffffffu, sx, 2 * h));
                         }
-                        aa[0] = __fadd_rn(aa[0], __shfl_xor_sync(0xffffffffu, aa[0], 1));
-                        cc[0] = __fadd_rn(cc[0], __shfl_xor_sync(0xffffffffu, cc[0], 1));
-                        ac[0] = __fadd_rn(ac[0], __shfl_xor_sync(0xffffffffu, ac[0], 1));
-                        float* rb = red + (itn & 1) * (4 * 48);
-                        if ((lane & 1) == 0) {
-                            float* o = rb + quarter * 48 + (lane >> 1) * 3;
-                            o[0] = aa[0]; o[1] = cc[0]; o[2] = ac[0];
-                        }
-                        asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");       // the 4 warps (lane quarters) of this unit
-                        if (quarter == 0 && lane < 16) {
-                            const int e = col0 + lane;
-                            if (e < valid && emit) {
-                                const float* o = rb + lane * 3;
-                                const float saa = __fadd_rn(__fadd_rn(o[0], o[48]), __fadd_rn(o[96], o[144]));
-                                const float scc = __fadd_rn(__fadd_rn(o[1], o[49]), __fadd_rn(o[97], o[145]));
-                                const float sac = __fadd_rn(__fadd_rn(o[2], o[50]), __fadd_rn(o[98], o[146]));
-                                const float n4 = fmaxf(sqrtf(saa), 1e-12f), n6 = fmaxf(sqrtf(scc), 1e-12f);
-                                const float a2 = __fdiv_rn(saa, __fmul_rn(n4, n4)), c2 = __fdiv_rn(scc, __fmul_rn(n6, n6));
-                                const float acn = __fdiv_rn(sac, __fmul_rn(n4, n6));
-                                const float s2w = __fadd_rn(__fadd_rn(c2, -2.f * acn), a2);
-                                W[e] = __fdiv_rn(1.f, sqrtf(fmaxf(s2w, 1e-30f)));
-                            }
+                    }
+                    aa[0] = __fadd_rn(aa[0], __shfl_xor_sync(0xffffffffu, aa[0], 1));
+                    cc[0] = __fadd_rn(cc[0], __shfl_xor_sync(0xffffffffu, cc[0], 1));
+                    ac[0] = __fadd_rn(ac[0], __shfl_xor_sync(0xffffffffu, ac[0], 1));
+                    float* rb = red + (itn & 1) * (4 * 48);
+                    if ((lane & 1) == 0) {
+                        float* op = rb + quarter * 48 + (lane >> 1) * 3;
+                        op[0] = aa[0]; op[1] = cc[0]; op[2] = ac[0];
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");       // the 4 warps (lane quarters) of this unit
+                    if (quarter == 0 && lane < 16) {
+                        if (lc + lane < valid && emit) {
+                            const float* op = rb + lane * 3;
+                            const float saa = __fadd_rn(__fadd_rn(op[0], op[48]), __fadd_rn(op[96], op[144]));
+                            const float scc = __fadd_rn(__fadd_rn(op[1], op[49]), __fadd_rn(op[97], op[145]));
+                            const float sac = __fadd_rn(__fadd_rn(op[2], op[50]), __fadd_rn(op[98], op[146]));
+                            const float n4 = fmaxf(sqrtf(saa), 1e-12f), n6 = fmaxf(sqrtf(scc), 1e-12f);
+                            const float a2 = __fdiv_rn(saa, __fmul_rn(n4, n4)), c2 = __fdiv_rn(scc, __fmul_rn(n6, n6));
+                            const float acn = __fdiv_rn(sac, __fmul_rn(n4, n6));
+                            const float s2w = __fadd_rn(__fadd_rn(c2, -2.f * acn), a2);
+                            W[lane] = __fdiv_rn(1.f, sqrtf(fmaxf(s2w, 1e-30f)));
                         }
                     }
                 }
             }
-            tc_fence_before();                                // the next dual's MMAs overwrite these columns
+            for (int o = 0; o < FOBJ; ++o)
+                if (!((mine >> o) & 1u)) (void)collect(o);    // (keeps this warp's view of every statistics barrier in step)
+            TR(0, 610);
+            tc_fence_before();                                // the next round's MMAs overwrite these columns
         }
     }
     tc_fence_before();
@@ -946,11 +1007,11 @@ namespace dcd {
 
 bool gmw_fused_supported(int n) {
     const int E = n * (n - 1) / 2;
-    return 8 * ((E + 127) / 128) <= FES_MAX;
+    return 16 * ((E + 16 * FCS - 1) / (16 * FCS)) <= FES_MAX;
 }
 
-constexpr int FMAX_GROUPS = 16;                               // exchange buffer sized for up to 256 SMs
-constexpr size_t kExchangeBytes = (size_t)FMAX_GROUPS * 2 * 2 * FCS * CH * sizeof(float2);    // [group][object half][slot][rank][128]
+constexpr int FMAX_GROUPS = 10;                               // exchange buffer sized for up to 256 SMs
+constexpr size_t kExchangeBytes = (size_t)FMAX_GROUPS * FOBJ * 2 * FCS * CH * sizeof(float2);    // [group][object][slot][rank][128]
 
 // Tail of the workspace used by the fused forward, per matrix m = (net, block, {folded preconv.conv1, conv2}):
 //   scales2 [4*depth] float2 (256-byte padded) | bias2 [4*depth][128] | weight image [4*depth][128][128] u32 | exchange buffer
@@ -989,9 +1050,12 @@ int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* pa
     if (max_groups < 1) return DCD_E_UNSUPPORTED;
     fused_prep_kernel<<<4 * depth, 1024, CH * CH * sizeof(float), st>>>(params4, params6, depth, a.fold, scales2, bias2, wimg);
     cudaMemsetAsync(xg, 0x80, kExchangeBytes, st);            // every word starts with the flag its first use does not expect
-    // work is dealt to the groups as object pairs (paired schedule: both nets of a pair back to back) or (pair, net) duals
-    const bool paired = reg_w != nullptr && a.L.N >= 2 * (int64_t)max_groups;
-    const int64_t npairs = (a.L.N + 1) / 2;
+    // work is dealt to the groups as object triples (paired schedule: both nets of a triple back to back; the first net's
+    // features are parked in one activation slot, FOBJ * FCS * ES columns per group) or as (triple, net) rounds
+    const int64_t es = 16 * ((a.L.E + 16 * FCS - 1) / (16 * FCS));
+    const bool paired = reg_w != nullptr && a.L.N >= FOBJ * (int64_t)max_groups &&
+                        a.L.N * (int64_t)a.L.EP >= (int64_t)max_groups * FOBJ * FCS * es;
+    const int64_t npairs = (a.L.N + FOBJ - 1) / FOBJ;
     const int64_t nitems = paired ? npairs : npairs * 2;
     const int ngroups = (int)(nitems < max_groups ? nitems : max_groups);
     MlpArgs args = a;

@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in trace trace6 oldtrace; do
-DCD_B200_LIB=$PWD/dcd_b200/libdcd_b200_$c.so TRACE_OBJECTS=8 timeout 120 python profiles/trace_fused.py > gpurun_out/h_$c.txt 2>&1
-echo "$c rc=$?"; wc -l gpurun_out/h_$c.txt
+for v in expw exps expws; do
+DCD_B200_LIB=$PWD/dcd_b200/libdcd_b200_$v.so timeout 200 python bench.py --steps 1 --warmup 3 --quick --no-cpu-baseline --frames 800 > gpurun_out/h_$v.json 2> gpurun_out/h_$v.err
+echo "$v rc=$? $(cut -c1-120 gpurun_out/h_$v.json)"; tail -2 gpurun_out/h_$v.err
 done
+timeout 200 python bench.py --steps 1 --warmup 3 --quick --no-cpu-baseline --frames 800 > gpurun_out/h_base.json 2> gpurun_out/h_base.err
+echo "base rc=$? $(cut -c1-120 gpurun_out/h_base.json)"

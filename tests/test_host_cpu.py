@@ -51,8 +51,8 @@ def test_version_strerror_and_size_queries(lib):
     acts_and_stats = 4 * (2 * 3 * 128 * T * 128 + 2 * 12 * 2 * T * 128 * 2)
     scales = 768                                         # 72 per-matrix (scale, 1/scale) pairs, 256-byte aligned
     # tail of the fused forward: 48 matrices (folded preconv.conv1 and conv2 per block and net): scales, biases, pre-split
-    # FP16 hi/lo weight image; then the statistics exchange buffer [group][object half][slot][rank][128] float2
-    image = 512 + 48 * 128 * 4 + 48 * 128 * 128 * 4 + 16 * 2 * 2 * 16 * 128 * 8
+    # FP16 hi/lo weight image; then the statistics exchange buffer [group][object][slot][rank][128] float2
+    image = 512 + 48 * 128 * 4 + 48 * 128 * 128 * 4 + 10 * 3 * 2 * 24 * 128 * 8
     image += 24 * (128 * 128 + 128) * 4 + 256            # folded preconv.conv1 layers (Wf^T, bf) + their running maxima
     assert lib.dcd_gmw_workspace_bytes(1, 73, 12, 0) == acts_and_stats + scales + image
     assert lib.dcd_gmw_workspace_bytes(0, 73, 12, 0) == 0
