@@ -26,6 +26,14 @@
 #include <type_traits>
 #include "gmw_tc_common.cuh"
 
+// back-off (ns) of the waits whose spinning competes with the warps being waited for; 0 = spin on the test
+#ifndef DCD_FUSED_STAT_SLEEP
+#define DCD_FUSED_STAT_SLEEP 40      // converters waiting for a layer's statistics
+#endif
+#ifndef DCD_FUSED_DONE_SLEEP
+#define DCD_FUSED_DONE_SLEEP 20      // converters waiting for an operand buffer
+#endif
+
 namespace dcd {
 // Optional in-kernel timeline (build with -DDCD_FUSED_TRACE, see profiles/trace_fused.py): lane 0 of converter warp 0
 // and of the MMA warp of CTA 0 record (tag, clock64) pairs; read back with dcd_debug_fused_trace().
@@ -117,7 +125,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(ns);
+        if (ns) __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -576,7 +584,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         uint32_t par = 0, pend = 0;                           // per operand buffer: next wait parity, MMA in flight
         auto wait_buf = [&](uint32_t b) {
             if ((pend >> b) & 1u) {
-                mbar_wait(bar + BAR_DONE0 + b, (par >> b) & 1u);
+                mbar_wait_backoff(bar + BAR_DONE0 + b, (par >> b) & 1u, DCD_FUSED_DONE_SLEEP);
                 par ^= 1u << b;
                 pend &= ~(1u << b);
                 tc_fence_after();
@@ -584,8 +592,13 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         };
         auto obj_of = [&](int u) { return (u >= upo ? 1 : 0) + (u >= 2 * upo ? 1 : 0); };
         uint32_t spar = 0;                                    // wait parities of the three statistics barriers (this warp's view)
-        uint32_t mine = 0;                                    // objects this warp has a unit of (all three unless the slices are tiny)
-        for (int u = wg; u < FOBJ * upo; u += 3) mine |= 1u << obj_of(u);
+        // tiles where this warp's unit is the first / the last one it has of an object (upo >= 3: every warp has units of all three)
+        uint32_t firstmask = 0, lastmask = 0;
+        for (int t = 0; t < ntile; ++t) {
+            const int u = 3 * t + wg;
+            if (t == 0 || obj_of(u) != obj_of(u - 3)) firstmask |= 1u << t;
+            if (t == ntile - 1 || obj_of(u + 3) != obj_of(u)) lastmask |= 1u << t;
+        }
         // unit stream of this warp's units of object o: (wg - o * upo) mod 3
         auto stream_of = [&](int o) { return (wg + 3 * o * upo - o * upo) % 3; };
 
@@ -653,16 +666,15 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
             conv_sync();                                      // the features are consumed: operand buffers free
             TR(0, 901);
 
-            // ---- the layers: a stream of steps (layer, tile)
+            // ---- the layers: a stream of steps (layer, tile).  This warp converts unit 3 t + wg of tile t; the units of an object are
+            //      consecutive, so the object and the offset inside its slice are running values (firstmask / lastmask: the tiles
+            //      where this warp's unit is its first / last of an object).
             float un_out = 0.f, b_out = 0.f, un_prev = 0.f, b_prev = 0.f;   // scale / bias of the matrices of this and the previous layer
             float un_next = __ldg(scales + mat_base).y, b_next = __ldg(bias2 + mat_base * CH + ch);       // (fetched one layer ahead)
-            int ph_now = 0;
-            int qa = -1, qb = -1;                             // tiles whose statistics are due (older, newer): tile | (layer & 1) << 9 | buffer << 10
-            int fin = 0;                                      // layers whose partial is posted, per object (8 bits each)
-            int o_post = 0;                                   // next object to post in the layer whose statistics are being accumulated
+            // the tile whose statistics are due next (two steps behind the conversion): tile, object, object's first column, parity of its layer
+            int npend = 0, t_e = 0, o_e = 0, ob_e = 0, p_e = 0;
             float K = 0.f, s1 = 0.f, s2 = 0.f, bK = 0.f;      // shifted sums of the layer output being accumulated (one object at a time)
             bool have_K = false;
-            bool cv_ready = false;                            // the next unit's accumulators are already in flight
             uint32_t cv[16], sv[16];
 
             // statistics of one unit from its raw accumulators (un, bb: scale and bias of the producing matrix), as sums shifted
@@ -673,7 +685,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     bK = bb - K;
                     have_K = true;
                 }
-                if (nv == 16) {
+                if (nv >= 16) {
                     float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
@@ -697,8 +709,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                         }
                 }
             };
-            // this unit stream's part of object o's layer output is complete (possibly empty): post its (mean, M2) for the
-            // statistics warps
+            // this unit stream's part of object o's layer output is complete: post its (mean, M2) for the statistics warps
             auto post = [&](int o) {
                 const int k = stream_of(o);
                 const float ic = tab_s[9 + o * 3 + k].x;
@@ -709,58 +720,38 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 TR(0, 603);
                 K = 0.f; s1 = 0.f; s2 = 0.f; bK = 0.f;
                 have_K = false;
-                fin += 1 << (8 * o);
             };
             // (mean, rstd) of object o's latest layer, handed back by the statistics warps in this warp's partial slot
             auto collect = [&](int o) {
                 TR(0, 606);
-#ifndef DCD_EXP_NO_STATWAIT
-                mbar_wait_backoff(bar + BAR_STAT0 + o, (spar >> o) & 1u, 40);
-#endif
+                mbar_wait_backoff(bar + BAR_STAT0 + o, (spar >> o) & 1u, DCD_FUSED_STAT_SLEEP);
                 spar ^= 1u << o;
                 TR(0, 608);
                 return pbuf[(o * 3 + stream_of(o)) * CH + ch];
             };
-
-            // statistics of the oldest pending tile; `wait`: its MMA is not yet known to be complete; `loaded`: its accumulators
-            // are already in sv (loaded and waited for by the step)
-            auto process_oldest = [&](bool wait, bool loaded) {
-                const int e = qa;
-                qa = qb;
-                qb = -1;
-                const int t_e = e & 0xff, pp = (e >> 9) & 1;
-                if (wait) wait_buf((uint32_t)(e >> 10) & 1u);
-                const int u_e = 3 * t_e + wg;
-                const int o_e = obj_of(u_e);
-                const int lc = 16 * (u_e - o_e * upo);
-                const int nv = min(16, valid - lc);
-                if (t_e == 0) o_post = 0;
-                const int layer_e = (pp == (ph_now & 1)) ? ph_now : ph_now - 1;
-                // (objects this stream has no unit of: an empty partial, once the previous layer's exchange of that object is over)
-                auto post_any = [&](int o) {
-                    if (!((mine >> o) & 1u) && layer_e > 0) (void)collect(o);
-                    post(o);
-                };
-                while (o_post < o_e) post_any(o_post++);
+            // statistics of the due tile (its MMA is complete; `loaded`: its accumulators are already in sv)
+            auto process_due = [&](bool loaded, int ph) {
+                const int cb = FSUB * t_e + 16 * wg;          // first column of the unit
+                const int nv = valid - (cb - ob_e);           // valid edges from the unit's first on
                 if (nv > 0) {
                     if (!loaded) {
-                        tmem_ld16_issue(t_lane + 16 * u_e, sv);
+                        tmem_ld16_issue(t_lane + cb, sv);
                         tmem_ld16_wait(sv);
                     }
-                    const bool cur = pp == (ph_now & 1);
+                    const bool cur = p_e == (ph & 1);
                     stats_math(sv, nv, cur ? un_out : un_prev, cur ? b_out : b_prev);
                 }
-                const int o_nx = (t_e + 1 < ntile) ? obj_of(u_e + 3) : FOBJ;
-                while (o_post < o_nx) post_any(o_post++);
+                if ((lastmask >> t_e) & 1u) post(o_e);
+                if (++t_e == ntile) {
+                    t_e = 0; o_e = 0; ob_e = 0; p_e ^= 1;
+                } else if ((firstmask >> t_e) & 1u) {
+                    ++o_e; ob_e += ES;
+                }
             };
-            auto ensure_posted = [&](int o, int need) {
-                while (((fin >> (8 * o)) & 0xff) < need && qa >= 0) process_oldest(true, false);
-            };
-            int o_cur = -1;                                   // object of the current input transform
+
             float a_in = 0.f, c_in = 0.f;
             for (int ph = 0; ph < nphase; ++ph) {
                 const int kind = (ph & 1) ? 2 : 0;            // 0: (residual update ->) folded preconv.conv1, 2: conv2
-                ph_now = ph;
                 un_prev = un_out;
                 b_prev = b_out;
                 un_out = un_next;
@@ -770,47 +761,42 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     b_next = __ldg(bias2 + (mat_base + ph + 1) * CH + ch);
                 }
                 const bool reads_d = ph > 0;
-                o_cur = -1;
-                // Software pipeline over the steps: the accumulators of the NEXT unit to convert (cv) and of the unit whose
-                // statistics are due (sv, two steps behind: its MMA is known complete when its operand buffer comes free)
-                // are in flight from tensor memory while the current unit is being processed.
+                // Software pipeline over the steps: the accumulators of the NEXT unit to convert (cv, issued at the end of the
+                // previous step) and of the unit whose statistics are due (sv, two steps behind: its MMA is known complete when
+                // its operand buffer comes free) are in flight from tensor memory while the current unit is being processed.
+                int o = 0, ob = 0;
                 for (int t = 0; t < ntile; ++t, ++g) {
-                    const int u = 3 * t + wg;                 // this warp's unit: columns [16 u, 16 u + 16) of the CTA
-                    const int o = obj_of(u);
-                    const int lc = 16 * (u - o * upo);        // first edge of the unit inside the object's slice
-                    if (reads_d && o != o_cur) {
-                        // input transform of this layer as one FMA on the raw accumulator: the context norm of the producing
-                        // layer folded in ((d*un + b - mean) * rstd)
-                        ensure_posted(o, ph);
-                        const float2 st = collect(o);
-                        a_in = un_prev * st.y;
-                        c_in = (b_prev - st.x) * st.y;
-                        o_cur = o;
+                    const int cb = FSUB * t + 16 * wg;        // this warp's unit: columns [cb, cb + 16) of the CTA
+                    if ((firstmask >> t) & 1u) {
+                        if (t > 0) { ++o; ob += ES; }
+                        if (reads_d) {
+                            // input transform of this layer as one FMA on the raw accumulator: the context norm of the producing
+                            // layer folded in ((d*un + b - mean) * rstd)
+                            const float2 st = collect(o);
+                            a_in = un_prev * st.y;
+                            c_in = (b_prev - st.x) * st.y;
+                        }
                     }
+                    const int lc = cb - ob;                   // first edge of the unit inside the object's slice
                     const uint32_t b = g & 1u;
                     TR(0, 1000 * kind + 100 + t);
                     wait_buf(b);
                     TRF(0, 1000 * kind + 200 + t);
                     unsigned char* b_hi = Bbuf + (size_t)b * 2 * FB_PART;
-                    if (reads_d && !cv_ready) tmem_ld16_issue(t_lane + 16 * u, cv);
                     // the tile of two steps ago (same operand buffer: its MMA is complete) is due for its statistics
-                    const bool due = qb >= 0;
-                    bool st_load = false;
-                    if (due) {
-                        const int u_e = 3 * (qa & 0xff) + wg;
-                        st_load = valid > 16 * (u_e - obj_of(u_e) * upo);
-                    }
+                    const bool due = npend == 2;
+                    const int cb_e = FSUB * t_e + 16 * wg;
+                    const bool st_load = due && valid > cb_e - ob_e;
                     float v[16];
-                    float4* Xp = Xs + (4 * u) * CH + ch;
+                    float4* Xp = Xs + (cb >> 2) * CH + ch;
                     float4 x4[4];
                     if (kind == 0) {
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4) x4[q4] = Xp[q4 * CH];
                     }
                     if (reads_d) tmem_ld16_wait(cv);
-                    cv_ready = false;
                     TRF(0, 1000 * kind + 300 + t);
-                    if (st_load) tmem_ld16_issue(t_lane + 16 * (3 * (qa & 0xff) + wg), sv);
+                    if (st_load) tmem_ld16_issue(t_lane + cb_e, sv);
                     if (kind == 0) {
                         if (reads_d) {
 #pragma unroll
@@ -852,32 +838,29 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     pend |= 1u << b;
                     TRF(0, 1000 * kind + 500 + t);
                     if (st_load) tmem_ld16_wait(sv);              // (before the next load is issued: the wait covers all loads in flight)
-                    // the next unit to convert: the next tile's, else the next layer's first (whose producing MMA is complete
-                    // when a layer has at least two tiles)
-                    {
-                        const bool cross = t + 1 == ntile;
-                        const int nu = cross ? wg : u + 3;
-                        const int nph = cross ? ph + 1 : ph;
-                        if (nph > 0 && nph < nphase && (!cross || ntile >= 2)) {
-                            tmem_ld16_issue(t_lane + 16 * nu, cv);
-                            cv_ready = true;
-                        }
+                    // the next unit to convert: the next tile's, else the next layer's first (whose producing MMA is long complete)
+                    if (t + 1 < ntile) {
+                        if (reads_d) tmem_ld16_issue(t_lane + cb + FSUB, cv);
+                    } else if (ph + 1 < nphase) {
+                        tmem_ld16_issue(t_lane + 16 * wg, cv);
                     }
-                    if (due) process_oldest(false, true);
-                    const int ent = t | ((ph & 1) << 9) | ((int)b << 10);
-                    if (qa < 0) qa = ent; else qb = ent;
+                    if (due) process_due(true, ph); else ++npend;
                 }
             }
             TR(0, 600);
 
             // ---- final features x = relu(cn(Y2)) + X of the three objects.  First the statistics still due (their MMAs are then
             //      complete and the operand buffers free for the epilogue's scratch).
-            ph_now = nphase;
+            wait_buf(0);
+            wait_buf(1);
             un_prev = un_out;
             b_prev = b_out;
-            while (qa >= 0) process_oldest(true, false);
+            while (npend > 0) {
+                process_due(false, nphase);
+                --npend;
+            }
             TR(0, 601);
-            o_cur = -1;
+            int o_cur = -1;
             float a_fin = 0.f, c_fin = 0.f;
             int itn = 0;
             for (int u = wg; u < FOBJ * upo; u += 3, ++itn) {
@@ -981,8 +964,6 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     }
                 }
             }
-            for (int o = 0; o < FOBJ; ++o)
-                if (!((mine >> o) & 1u)) (void)collect(o);    // (keeps this warp's view of every statistics barrier in step)
             TR(0, 610);
             tc_fence_before();                                // the next round's MMAs overwrite these columns
         }
@@ -1007,7 +988,8 @@ namespace dcd {
 
 bool gmw_fused_supported(int n) {
     const int E = n * (n - 1) / 2;
-    return 16 * ((E + 16 * FCS - 1) / (16 * FCS)) <= FES_MAX;
+    const int upo = (E + 16 * FCS - 1) / (16 * FCS);          // 16-edge units per object and CTA
+    return upo >= 3 && 16 * upo <= FES_MAX;                  // (below 3 a converter warp would not see every object: layer-wise kernels)
 }
 
 constexpr int FMAX_GROUPS = 10;                               // exchange buffer sized for up to 256 SMs
