@@ -484,7 +484,7 @@ def run_kitti_val(args):
         e2e_value = N_total * args.steps / (e2e_ms * 1e-3)
         mlp_tflops = F_MLP * mlp_objs / (mlp_ms * 1e-3) / 1e12
         n_mlp_launches = len(fw.mlp_events)
-        out_bytes = 2 * 128 * 128 * ((EDGES + 127) // 128) * 4            # final features of both nets, per object
+        out_bytes = EDGES * 4 + N_KPTS * 20                               # per object: keypoints in, edge weights out (paired schedule)
         traffic = measured_traffic("mlp_fused_kernel") if chunk == 2048 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -496,20 +496,22 @@ def run_kitti_val(args):
                                                                               "U{1..50}" if ragged else "50", N,
                                                                               ", + all-gather of depths" if world > 1 else ""),
                        "objects_per_gpu": N, "objects_total": N_total, "chunk_objects": chunk, "net_depth": DEPTH,
-                       "l2_policy": "every chunk streams %.1f GB of final features through L2 (126 MB): nothing survives between "
-                                    "chunks or steps" % (min(chunk, N) * 2 * 128 * 128 * ((EDGES + 127) // 128) * 4 / 1e9),
+                       "l2_policy": "inputs larger than L2: a step reads %.0f MB of keypoints and writes %.0f MB of edge weights + depths per "
+                                    "GPU against 126 MB of L2; per chunk the kernel also parks 25 MB of 4-d features in L2" % (
+                                        N * (N_KPTS * 20 + 4) / 1e6, N * (EDGES * 4 + 4) / 1e6),
                        "weights": "random init, seed %d, reference state_dict layout" % WEIGHT_SEED},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": N * 4,
                     "api": "dcd_b200.gmw_weighted_depth on pinned host tensors"},
             "gpu_launches": timed_launches,
-            "roofline": {"kernel": "mlp_fused_kernel (edge-feature MLP, the whole net of an object in one launch by a group of 8 co-resident CTAs: activations "
-                                   "stay in shared/tensor memory; preconv.conv1 folded: 24 GEMM layers x 2 nets on tcgen05, FP16x3 split, FP32 accumulate "
-                                   "in TMEM)",
+            "roofline": {"kernel": "mlp_fused_kernel (edge-feature MLP, the whole net in one launch: groups of 24 co-resident CTAs work on three objects "
+                                   "at a time, activations stay in shared/tensor memory, one object's context-norm exchange runs behind the other two's "
+                                   "tiles; preconv.conv1 folded: 24 GEMM layers x 2 nets on tcgen05, FP16x3 split, FP32 accumulate in TMEM; the "
+                                   "edge weights come out of the kernel's own epilogue)",
                          "bound": "tensor",
                          "achieved": mlp_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": mlp_tflops / peaks["bf16_tflops_sustained"],
                          # ncu dram__bytes_read+write of ONE mlp_fused_kernel launch on a 2048-object chunk, from the committed
-                         # capture of this build (profiles/traffic.json); algorithmic: 2048 x 2.75 MB of final features out
+                         # capture of this build (profiles/traffic.json); algorithmic: 2048 x 12 KB (keypoints in, edge weights out)
                          "traffic": traffic,
                          "peak_source": "%s dense bf16 (sustained, of measured); `achieved` counts the algorithmic FP32 GEMM FLOPs, the "
                                         "tensor pipe executes 3 FP16 MMAs per FP32 product (x3 = %.1f TFLOP/s issued); vs the FP32 "

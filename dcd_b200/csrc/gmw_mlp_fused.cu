@@ -1,34 +1,46 @@
 // GMW edge-feature MLP forward, inference form: ONE kernel for the whole net (conv_in + 12 blocks; each block's
-// preconv and conv1 folded into one layer: 1 + 24 layers instead of 1 + 36), the object's activations never leave
+// preconv and conv1 folded into one layer: 1 + 24 layers instead of 1 + 36), the objects' activations never leave
 // the chip (sm_100a: tcgen05 + TMEM, persistent co-resident CTA groups).
 //
 // The layer-wise kernels (gmw_mlp_tc.cu) are bound by HBM: every context norm needs the statistics of the
 // whole object, so each of the 24 normalised layers writes its output and reads it back (198 MB / object).
-// Here a group of 8 CTAs owns one (object, net): CTA r holds the edge slice [r*ES, (r+1)*ES) of ALL 128
-// channels on chip for the whole network, and the only thing the CTAs exchange per context norm is the
-// per-channel (mean, M2) partial of their slice (1 KB per CTA, through L2 with self-validating words: no
-// fences, no barriers).  Groups are plain consecutive CTAs of a cooperative launch (all CTAs resident, one per
-// SM): 18 groups use 144 of the 148 SMs, where hardware clusters of 8 can only be placed on 120.
-// Per CTA (ES <= 336 edges, E <= 2688, i.e. up to the reference's n = 73 keypoints):
-//   * residual stream X        : FP32 in shared memory, [ES/4][128 ch] float4            (172 KB)
-//   * layer output (P, Y1, Y2) : FP32 accumulators in tensor memory, columns [0, ES)     (336 of 512 columns);
-//                                every GEMM overwrites its own input sub-tile in place
+// Here a group of 24 CTAs works on THREE objects of one net at a time: CTA r holds the edge slice [r*ES, (r+1)*ES)
+// of each of them (ES <= 112) for ALL 128 channels on chip for the whole network, the three slices side by side
+// (3 ES = 336 columns = 7 MMA tiles of 48 edges per layer).  The only thing the CTAs exchange per context norm is
+// the per-channel (mean, M2) partial of a slice (1 KB per CTA and object, through L2 with self-validating words:
+// no fences, no barriers) — and because the three objects follow each other through every layer, one object's
+// exchange (the drain of its last MMAs, the L2 round trip between 24 CTAs, the merge) runs behind the other two
+// objects' tiles instead of idling the tensor pipe at the end of every layer; the layer weights are fetched once
+// for three objects.  Groups are plain consecutive CTAs of a cooperative launch (all CTAs resident, one per SM):
+// 6 groups use 144 of the 148 SMs.
+// Per CTA (E <= 2688, i.e. up to the reference's n = 73 keypoints; at least 3 units of 16 edges per slice, n >= 40):
+//   * residual stream X        : FP32 in shared memory, [3 ES/4][128 ch] float4          (172 KB)
+//   * layer output (P, Y1, Y2) : FP32 accumulators in tensor memory, columns [0, 3 ES)   (336 of 512 columns);
+//                                every GEMM overwrites its own input tile in place
 //   * weights                  : FP16 hi/lo pairs as the A operand in tensor memory, columns [384, 512),
 //                                reloaded per layer from an L2-resident pre-split image (64 KB / layer)
-//   * B operand                : two 24 KB buffers (hi + lo of a 48-edge sub-tile, MN-major, no swizzle),
+//   * B operand                : two 24 KB buffers (hi + lo of a 48-edge tile, MN-major, no swizzle),
 //                                written by the threads that produce the values (thread = channel)
-// Warp roles: 12 converter warps (thread = channel; accumulators -> context norm / ReLU / residual -> FP16
-// hi/lo operand; statistics of the layer output), 4 service warps (weight image -> tensor memory; the first one
-// issues the MMAs from an elected lane).  Hand-offs are mbarriers; there is no CTA-wide barrier per sub-tile.
+// Warp roles: 12 converter warps (thread = channel, a warp converts one 16-edge unit per tile: accumulators ->
+// context norm / ReLU / residual -> FP16 hi/lo operand; statistics of the layer output two tiles behind), the MMA
+// warp (weights of its lane quarter -> tensor memory; tcgen05.mma from an elected lane), 3 statistics warps (weights
+// of their lane quarters; publish / collect / merge the slices' statistics and hand (mean, rstd) back).  Hand-offs
+// are mbarriers and named barriers; there is no CTA-wide barrier per tile.  Waits that would spin against the
+// warps being waited for back off (nanosleep): the statistics warps are the shortest resource of the kernel.
 // Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, FP32 statistics) up to
-// the folded layer (Wf = W1.Wp formed in FP64, rounded once) and the order in which the statistics partials are merged.
-// HBM traffic: keypoints in, final features out (2.75 MB / object instead of 198 MB).
+// the folded layer (Wf = W1.Wp formed in FP64, rounded once), the shifted-sum form of the slice statistics, rsqrtf for
+// the reciprocal standard deviation and the order in which the partials are merged (fixed: results are bit-identical
+// whichever place of a triple, chunk or schedule an object takes).
+// HBM traffic: keypoints in, edge weights out (paired schedule) or final features out (2.75 MB / object).
 #include <type_traits>
 #include "gmw_tc_common.cuh"
 
 // back-off (ns) of the waits whose spinning competes with the warps being waited for; 0 = spin on the test
 #ifndef DCD_FUSED_STAT_SLEEP
 #define DCD_FUSED_STAT_SLEEP 40      // converters waiting for a layer's statistics
+#endif
+#ifndef DCD_FUSED_POLL_GRACE
+#define DCD_FUSED_POLL_GRACE 500    // statistics warps: pause between publishing a slice and the first look at the others'
 #endif
 #ifndef DCD_FUSED_DONE_SLEEP
 #define DCD_FUSED_DONE_SLEEP 20      // converters waiting for an operand buffer
@@ -423,20 +435,27 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
             TR(2, 710 + o);
             float2* xrow0 = ev_row(o);
             const uint32_t flag = ev_flag(o);
-            for (int rep = 0; rep < nrep; ++rep) {
-                const int c = rep ? 96 + lane : 32 * (warp - FCONV_WARPS - 1) + lane;
-                float2 q[3];
+            float2 tb[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) q[k] = pbuf[(o * 3 + k) * CH + c];
+            for (int k = 0; k < 3; ++k) tb[k] = tab_s[o * 3 + k];
+            const int c0 = 32 * (warp - FCONV_WARPS - 1) + lane, c1 = 96 + lane;       // (the second channel: first statistics warp only)
+            float2 q[2][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                q[0][k] = pbuf[(o * 3 + k) * CH + c0];
+                q[1][k] = pbuf[(o * 3 + k) * CH + c1];
+            }
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
                 float m = 0.f, M2 = 0.f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) m = fmaf(tab_s[o * 3 + k].y, q[k].x, m);
+                for (int k = 0; k < 3; ++k) m = fmaf(tb[k].y, q[rep][k].x, m);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float nk = tab_s[o * 3 + k].x, dd = q[k].x - m;
-                    if (nk > 0.f) M2 += fmaf(nk * dd, dd, q[k].y);
+                    const float dd = q[rep][k].x - m;
+                    if (tb[k].x > 0.f) M2 += fmaf(tb[k].x * dd, dd, q[rep][k].y);
                 }
-                st_flagged(xrow0 + rank * CH + c, m, M2, flag);
+                if (rep < nrep) st_flagged(xrow0 + rank * CH + (rep ? c1 : c0), m, M2, flag);
             }
             TR(2, 720 + o);
         };
@@ -444,10 +463,12 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         // ranks for all 128 channels (a lane: 4 channels x 8 flagged words in flight at once, re-read until every word carries
         // this exchange's flag) and merges them; the three subset results meet in the object's partial slots, then every channel
         // is finished by one thread (rank subsets in order: the same operations in every CTA of the group).
-        auto ev_finish = [&](int o) {
+        auto ev_finish = [&](int o, bool fresh) {
             const int sb = warp - FCONV_WARPS - 1;            // rank subset of this warp: ranks 8 sb .. 8 sb + 7
             const float2* xrow0 = ev_row(o) + (size_t)(8 * sb) * CH + lane;
             const uint32_t flag = ev_flag(o);
+            // (right after this CTA's own publication the other slices cannot be visible yet: a first look would be wasted)
+            if (fresh) __nanosleep(DCD_FUSED_POLL_GRACE);
             float2 v[4][8];
             for (;;) {
 #pragma unroll
@@ -536,11 +557,11 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     // the next weights are due: they go first, the slices are collected afterwards.
                     if (ph > 0) {
                         ev_publish(2);
-                        ev_finish(2);
+                        ev_finish(2, true);
                     }
                     if (ph == nphase) break;
                     ev_publish(0);
-                    ev_finish(0);
+                    ev_finish(0, true);
                     ev_publish(1);
                 }
                 wpar ^= 1u;
@@ -570,7 +591,7 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                     mbar_wait(bar + BAR_PDONE, ppar);
                 }
                 ppar ^= 1u;
-                if (warp != FCONV_WARPS) ev_finish(1);
+                if (warp != FCONV_WARPS) ev_finish(1, false);
             }
         }
     } else {

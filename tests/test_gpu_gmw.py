@@ -175,12 +175,13 @@ def test_weight_gradients_full_size_vs_reference_fixture(golden):
 
 @pytest.mark.parametrize("n,depth,N", [(73, 12, 5), (60, 3, 3), (8, 2, 9), (17, 1, 1), (74, 2, 2), (73, 12, 41), (60, 2, 37), (20, 3, 19)])
 def test_fused_inference_forward_agrees_with_layerwise_training_forward(n, depth, N):
-    """Inference (no grad) runs the whole network in one cluster kernel with the activations on chip; the
-    training forward runs layer by layer through HBM.  Same arithmetic, different merge order of the context-norm
-    partials: the two must agree to FP32 rounding.  n = 74 exceeds the on-chip capacity and takes the layer-wise
-    kernels in both modes.  With at least as many objects as CTA groups (18 on a B200) the fused kernel runs its PAIRED
-    schedule and emits the edge weights from its own epilogue (no feature round trip through HBM); below that the
-    features go through gmw_edge_weight_kernel."""
+    """Inference (no grad) runs the whole network in one kernel with the activations on chip (n = 40 .. 73: three
+    objects per group of 24 CTAs); the training forward runs layer by layer through HBM.  Same arithmetic, different
+    merge order of the context-norm partials: the two must agree to FP32 rounding.  n = 74 exceeds the on-chip capacity,
+    n < 40 leaves a converter warp without a unit of every object: both take the layer-wise kernels in both modes.  With
+    at least three objects per CTA group (18 on a B200) the fused kernel runs its PAIRED schedule and emits the edge
+    weights from its own epilogue (no feature round trip through HBM); below that the features go through
+    gmw_edge_weight_kernel."""
     ob = synth.make_objects(N=N, n=n, seed=900 + n)
     sd = O.random_state_dict(50 + n, depth=depth)
     model = make_model(sd, depth)
@@ -201,6 +202,28 @@ def test_fused_inference_forward_agrees_with_layerwise_training_forward(n, depth
         with torch.no_grad():
             w_few, _ = model(k2[:7].contiguous(), k3[:7].contiguous())
         assert rel_err(w_few, w_inf[:7]) < 1e-5         # (the paired epilogue sums the squares before normalising)
+
+
+@pytest.mark.parametrize("n,N,step", [(73, 20, 7), (73, 23, 5), (60, 22, 4), (73, 303, 17)])
+def test_fused_forward_is_independent_of_place_and_schedule(n, N, step):
+    """The on-chip forward works on three objects at a time and deals triples to the CTA groups; an object's weights must
+    not depend on its place in a triple, on the incomplete last triple (N % 3 != 0 repeats the last object), on the
+    schedule (paired for N >= 18, else through the feature buffer) or on how long the kernel has been running (N = 303:
+    more than 256 statistics exchanges per group, the flagged exchange words wrap many times): bit-identical weights
+    for the whole batch and for the same objects fed in small chunks at shifted positions."""
+    depth = 12 if N < 100 else 2
+    ob = synth.make_objects(N=N, n=n, seed=1000 + N)
+    model = make_model(O.random_state_dict(77, depth=depth), depth)
+    k2, k3 = cu(ob.kps_norm, ob.kps_3d)
+    with torch.no_grad():
+        w_all, _ = model(k2, k3)
+        w_again, _ = model(k2, k3)
+        parts = [model(k2[i:i + step].contiguous(), k3[i:i + step].contiguous())[0] for i in range(0, N, step)]
+    assert torch.equal(w_all, w_again)
+    assert torch.equal(w_all, torch.cat(parts))
+    sd64 = {k: v.double().to(DEV) for k, v in O.random_state_dict(77, depth=depth).items()}
+    w64 = O.gmw_reg_weights(k2[-2:].double(), k3[-2:].double(), sd64, depth)      # the last (incomplete) triple against FP64
+    assert rel_err(w_all[-2:], w64) < 2e-4
 
 
 def test_state_dict_round_trip():
