@@ -108,16 +108,21 @@ enum { NB_PART0 = 5, NB_STATW = 8 };
 constexpr int FSTAT_THREADS = 96;
 constexpr int NB_THREADS = FCONV_THREADS + FSTAT_THREADS;
 
-// Statistics exchange between the 8 CTAs of a group through global memory (L2): every published 8-byte word carries
+// Statistics exchange between the 24 CTAs of a group through global memory (L2): every published 8-byte word carries
 // its own "ready" flag in the sign bit of its second float (an M2 is never negative), so there are no fences, no
 // barriers and no ordering requirements: a reader re-reads a word until the flag matches the expected use count.
 __device__ __forceinline__ void st_flagged(float2* dst, float a, float b, uint32_t flag) {
     const uint32_t bits = (__float_as_uint(b) & 0x7fffffffu) | (flag << 31);
-    asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(__uint_as_float(bits)) : "memory");
+    // one 64-bit access at GPU scope (the words never leave this device; `volatile` would be system scope)
+    const unsigned long long w = ((unsigned long long)bits << 32) | (unsigned long long)__float_as_uint(a);
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
 }
 __device__ __forceinline__ float2 ld_volatile_f2(const float2* p) {
     float2 v;
-    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    v.x = __uint_as_float((uint32_t)w);
+    v.y = __uint_as_float((uint32_t)(w >> 32));
     return v;
 }
 // weight image: read-only, re-read by every CTA for every layer -> keep it in L2 against the streamed outputs
