@@ -59,6 +59,17 @@ def main():
                                                                                  ro["backward_ms_per_step"], ro["achieved"], ro["frac"],
                                                                                  l["stages"]["dgde_train_pattern_n256"]["objects_per_s"]))
         out.append("")
+    later = sorted(glob.glob(os.path.join(HERE, "r02_runs", "three_object_kernel", "bench_*gpu.json")))
+    if later:
+        out += ["## Later in the round: the three-objects-per-group inference kernel (single GPU)", "",
+                "The multi-GPU lines above were taken with the single-object fused kernel (48.7 k objects/s per GPU); objects are",
+                "independent, so only the per-GPU rate changes.  Re-measured on one GPU with the final kernel:", "",
+                "| config | objects/s | e2e objects/s | s per step |", "|---|---:|---:|---:|"]
+        for f in later:
+            l = load(f)
+            out.append("| %s | %.0f | %.0f | %.3f |" % (os.path.basename(f)[len("bench_"):-len("_1gpu.json")], l["value"], l["e2e"]["value"],
+                                                       l["ms_per_step"] / 1e3))
+        out.append("")
     open(os.path.join(HERE, "r02_scaling.md"), "w").write("\n".join(out))
     print("\n".join(out))
 
