@@ -39,6 +39,9 @@
 #ifndef DCD_FUSED_STAT_SLEEP
 #define DCD_FUSED_STAT_SLEEP 40      // converters waiting for a layer's statistics
 #endif
+#ifndef DCD_FUSED_CONV_FINAL
+#define DCD_FUSED_CONV_FINAL 1       // 1: the last merge of a context norm's statistics runs on the converter threads
+#endif
 #ifndef DCD_FUSED_POLL_GRACE
 #define DCD_FUSED_POLL_GRACE 500    // statistics warps: pause between publishing a slice and the first look at the others'
 #endif
@@ -322,6 +325,10 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
     const int ES = 16 * upo;                                 // edges per CTA and object
     const int ntile = upo;                                   // 48-column tiles of the CTA: FOBJ * ES == 48 * upo
     const int nphase = 2 * depth;                            // per block: folded preconv.conv1, conv2
+#if DCD_FUSED_CONV_FINAL
+    // (slices of 4 units: a converter warp's next post could overtake another warp's read of the shared partial slots)
+    const bool conv_final = upo != 4;
+#endif
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* Xs = reinterpret_cast<float4*>(smem + SMF_X);
@@ -500,6 +507,15 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 }
                 pbuf[(o * 3 + sb) * CH + 32 * q + lane] = make_float2(mu, M2);
             }
+#if DCD_FUSED_CONV_FINAL
+            if (conv_final) {                                 // the converter threads finish their channel themselves (see `collect`)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + BAR_STAT0 + o);
+                TR(2, 730 + o);
+                sxc = (sxc & ~(3u << (2 * o))) | (((((sxc >> (2 * o)) & 3u) + 1u) & 3u) << (2 * o));
+                return;
+            }
+#endif
             nbar_sync(NB_STATW, FSTAT_THREADS);
             for (int rep = 0; rep < nrep; ++rep) {
                 const int c = rep ? 96 + lane : 32 * sb + lane;
@@ -618,6 +634,9 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
         };
         auto obj_of = [&](int u) { return (u >= upo ? 1 : 0) + (u >= 2 * upo ? 1 : 0); };
         uint32_t spar = 0;                                    // wait parities of the three statistics barriers (this warp's view)
+#if DCD_FUSED_CONV_FINAL
+        const float inv_em1_c = 1.0f / (float)(E - 1);
+#endif
         // tiles where this warp's unit is the first / the last one it has of an object (upo >= 3: every warp has units of all three)
         uint32_t firstmask = 0, lastmask = 0;
         for (int t = 0; t < ntile; ++t) {
@@ -753,6 +772,24 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 mbar_wait_backoff(bar + BAR_STAT0 + o, (spar >> o) & 1u, DCD_FUSED_STAT_SLEEP);
                 spar ^= 1u << o;
                 TR(0, 608);
+#if DCD_FUSED_CONV_FINAL
+                if (conv_final) {
+                    // the three rank-subset results of this channel -> (mean, rstd): the very operations of the statistics
+                    // warps' last stage, done by the 384 converter threads instead of 96 statistics threads one after the other
+                    float2 q[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) q[k] = pbuf[(o * 3 + k) * CH + ch];
+                    float m = 0.f, M2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) m = fmaf(tab_s[56 + k].y, q[k].x, m);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float dd = q[k].x - m;
+                        M2 += fmaf(tab_s[56 + k].x * dd, dd, q[k].y);
+                    }
+                    return make_float2(m, rsqrtf(M2 * inv_em1_c + 1e-3f));
+                }
+#endif
                 return pbuf[(o * 3 + stream_of(o)) * CH + ch];
             };
             // statistics of the due tile (its MMA is complete; `loaded`: its accumulators are already in sv)
