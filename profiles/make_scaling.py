@@ -63,12 +63,13 @@ def main():
     if later:
         out += ["## Later in the round: the three-objects-per-group inference kernel (single GPU)", "",
                 "The multi-GPU lines above were taken with the single-object fused kernel (48.7 k objects/s per GPU); objects are",
-                "independent, so only the per-GPU rate changes.  Re-measured on one GPU with the final kernel:", "",
-                "| config | objects/s | e2e objects/s | s per step |", "|---|---:|---:|---:|"]
+                "independent, so only the per-GPU rate changes.  Re-measured with the final kernel (kitti_val at 2 GPUs: weak scaling,",
+                "the line the driver's scaling run prints; rank 1's shard recomputed on rank 0: bit-identical):", "",
+                "| config | GPUs | objects/s | e2e objects/s | s per step |", "|---|---:|---:|---:|---:|"]
         for f in later:
             l = load(f)
-            out.append("| %s | %.0f | %.0f | %.3f |" % (os.path.basename(f)[len("bench_"):-len("_1gpu.json")], l["value"], l["e2e"]["value"],
-                                                       l["ms_per_step"] / 1e3))
+            out.append("| %s | %d | %.0f | %.0f | %.3f |" % (os.path.basename(f)[len("bench_"):].rsplit("_", 1)[0], l["n_gpus"], l["value"],
+                                                            l["e2e"]["value"], l["ms_per_step"] / 1e3))
         out.append("")
     open(os.path.join(HERE, "r02_scaling.md"), "w").write("\n".join(out))
     print("\n".join(out))
