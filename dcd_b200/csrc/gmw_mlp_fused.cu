@@ -51,7 +51,8 @@
 
 namespace dcd {
 // Optional in-kernel timeline (build with -DDCD_FUSED_TRACE, see profiles/trace_fused.py): lane 0 of converter warp 0
-// and of the MMA warp of CTA 0 record (tag, clock64) pairs; read back with dcd_debug_fused_trace().
+// and of the MMA warp and the first statistics warp of CTA 0 record (tag, clock64) pairs; read back with dcd_debug_fused_trace().
+// -DDCD_FUSED_TRACE=2 adds the fine-grained tags (each costs ~100 clk: the coarse level keeps the timeline honest).
 #ifdef DCD_FUSED_TRACE
 __device__ long long g_trace[12288];
 __device__ int g_trace_n[3];
@@ -1067,9 +1068,9 @@ size_t gmw_fused_image_bytes(int depth) {
     return fused_scales_bytes(depth) + fused_bias_bytes(depth) + fused_image_only_bytes(depth) + kExchangeBytes;
 }
 
-// Runs both nets of all objects.  reg_w != nullptr and at least as many objects as groups: PAIRED schedule, the kernel emits
+// Runs both nets of all objects.  reg_w != nullptr and at least three objects per group: PAIRED schedule, the kernel emits
 // the edge weights itself (*emitted = true; nothing but reg_w is written to HBM; the first net's features are parked in the
-// otherwise unused SLOT_Y1 area of the inference workspace, one object's worth per group, which stays in L2).  Otherwise the
+// otherwise unused SLOT_Y1 area of the inference workspace, three slices per CTA, which stays in L2).  Otherwise the
 // final features land in SLOT_X of the workspace (*emitted = false) for gmw_edge_weight_kernel / the correspondence branch.
 // `tail` points to gmw_fused_image_bytes(depth) bytes (256-byte aligned).
 int launch_gmw_fused_fwd(const MlpArgs& a, const float* params4, const float* params6, void* tail, float* reg_w, bool* emitted,
