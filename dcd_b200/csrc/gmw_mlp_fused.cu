@@ -470,6 +470,8 @@ mlp_fused_kernel(MlpArgs a, const float2* __restrict__ scales, const float* __re
                 }
                 if (rep < nrep) st_flagged(xrow0 + rank * CH + (rep ? c1 : c0), m, M2, flag);
             }
+            // every post of this (object, layer) is consumed before any statistics warp reuses the partial slots (ev_finish)
+            nbar_sync(NB_STATW, FSTAT_THREADS);
             TR(2, 720 + o);
         };
         // Collect the 24 slices (the own one included) and hand (mean, rstd) to the converters.  Each statistics warp takes 8
