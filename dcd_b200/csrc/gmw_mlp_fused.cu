@@ -24,7 +24,8 @@
 // Warp roles: 12 converter warps (thread = channel, a warp converts one 16-edge unit per tile: accumulators ->
 // context norm / ReLU / residual -> FP16 hi/lo operand; statistics of the layer output two tiles behind), the MMA
 // warp (weights of its lane quarter -> tensor memory; tcgen05.mma from an elected lane), 3 statistics warps (weights
-// of their lane quarters; publish / collect / merge the slices' statistics and hand (mean, rstd) back).  Hand-offs
+// of their lane quarters; publish / collect / merge the slices' statistics and hand the three rank-subset results back:
+// the converter threads finish (mean, rstd) of their channel themselves when they pick them up).  Hand-offs
 // are mbarriers and named barriers; there is no CTA-wide barrier per tile.  Waits that would spin against the
 // warps being waited for back off (nanosleep): the statistics warps are the shortest resource of the kernel.
 // Arithmetic is the one of the layer-wise kernels (FP16x3 split, power-of-two weight scaling, FP32 statistics) up to
